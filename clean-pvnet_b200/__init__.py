@@ -1,0 +1,24 @@
+"""clean-pvnet_b200 -- B200-native RANSAC voting layer (drop-in for clean-pvnet's lib/csrc/ransac_voting).
+
+The directory name carries a hyphen (it is the project name); import it as
+`clean_pvnet_b200` (a tiny alias package at the repo root) or load it by path.
+
+Public surface (same names/signatures as the reference):
+    ransac_voting_gpu.ransac_voting_layer / ransac_voting_layer_v3 / estimate_voting_distribution_with_mean
+    ransac_voting.generate_hypothesis / voting_for_hypothesis / *_vanishing_point   (the pybind twins)
+"""
+from . import _lib  # noqa: F401
+from . import ransac_voting  # noqa: F401
+from . import ransac_voting_gpu  # noqa: F401
+from .ransac_voting_gpu import (  # noqa: F401
+    estimate_voting_distribution_with_mean,
+    ransac_voting_layer,
+    ransac_voting_layer_v3,
+    ransac_voting_layer_v3_host,
+    install_as_reference_module,
+)
+
+__all__ = [
+    "ransac_voting_layer", "ransac_voting_layer_v3", "estimate_voting_distribution_with_mean",
+    "ransac_voting_layer_v3_host", "install_as_reference_module", "ransac_voting", "ransac_voting_gpu",
+]

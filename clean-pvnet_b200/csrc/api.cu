@@ -1,0 +1,408 @@
+// api.cu -- the C ABI declared in include/pvnet_vote_b200.h.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "kernels.h"
+
+using namespace pvb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(PVB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int default_capacity(const pvb_desc *d)
+{
+    const long long HW = (long long)d->H * d->W;
+    long long cap = d->capacity;
+    if (cap <= 0) {
+        const long long mn = d->max_num < 0 ? 0 : d->max_num;
+        cap = mn + (long long)ceil(8.0 * sqrt((double)mn)) + 64;
+    }
+    if (cap > HW) cap = HW;
+    cap = (cap + 31) / 32 * 32;
+    return (int)cap;
+}
+
+int check_desc(const pvb_desc *d)
+{
+    if (!d) return fail(PVB_ERR_INVALID, "descriptor is NULL");
+    if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->K <= 0 || d->hn <= 0)
+        return fail(PVB_ERR_INVALID, "bad shape B=%d H=%d W=%d K=%d hn=%d", d->B, d->H, d->W, d->K, d->hn);
+    if ((long long)d->H * d->W > (1ll << 30)) return fail(PVB_ERR_INVALID, "image too large (H*W > 2^30)");
+    if (d->B > 65535 || d->K > 65535) return fail(PVB_ERR_INVALID, "B and K must be <= 65535");
+    if ((long long)d->K * ((d->hn + 511) / 512) > 65535) return fail(PVB_ERR_INVALID, "K*ceil(hn/512) must be <= 65535");
+    if (d->mask_dtype < PVB_MASK_U8 || d->mask_dtype > PVB_MASK_F64) return fail(PVB_ERR_INVALID, "bad mask_dtype %d", d->mask_dtype);
+    if (d->select_mode != PVB_SELECT_BYTE && d->select_mode != PVB_SELECT_EQ1)
+        return fail(PVB_ERR_INVALID, "bad select_mode %d", d->select_mode);
+    return PVB_OK;
+}
+
+int make_layout(const pvb_desc *d, pvb_layout *L)
+{
+    const int rc = check_desc(d);
+    if (rc) return rc;
+    const size_t B = (size_t)d->B, K = (size_t)d->K, hn = (size_t)d->hn;
+    const int nwords = (int)(((long long)d->H * d->W + 31) / 32);
+    const int cap = default_capacity(d);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes); return o; };
+    L->status = take(4 * sizeof(int));
+    L->fgsum = take(B * sizeof(unsigned long long));
+    L->nz = take(B * sizeof(int));
+    L->tn = take(B * sizeof(int));
+    L->state = take(B * sizeof(int));
+    L->bits = take(B * nwords * sizeof(uint32_t));
+    L->wordoff = take(B * nwords * sizeof(int));
+    L->xy = take(B * cap * sizeof(float2));
+    L->dirs = take(B * K * cap * sizeof(float2));
+    L->hyp = take(B * K * hn * sizeof(float2));
+    L->counts = take(B * K * hn * sizeof(int));
+    L->win = take(B * K * sizeof(float2));
+    L->total = off;
+    L->nwords = nwords;
+    L->capacity = cap;
+    return PVB_OK;
+}
+
+struct Plan {
+    pvb_layout L;
+    SelectArgs s;
+    VoteArgs v;
+    float2 *win;
+};
+
+int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
+              const float *selection, void *ws, size_t ws_bytes, uint32_t tag_idx, uint32_t tag_sel, Plan *P)
+{
+    int rc = make_layout(d, &P->L);
+    if (rc) return rc;
+    if (!mask || !vertex) return fail(PVB_ERR_INVALID, "mask/vertex is NULL");
+    if (!ws || ws_bytes < P->L.total) return fail(PVB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", P->L.total, ws_bytes);
+    if (reinterpret_cast<uintptr_t>(ws) & 255u) return fail(PVB_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    char *w = static_cast<char *>(ws);
+    const pvb_layout &L = P->L;
+    SelectArgs &s = P->s;
+    s.mask = mask; s.mask_dtype = d->mask_dtype; s.select_mode = d->select_mode;
+    s.msb = d->mask_stride[0]; s.msy = d->mask_stride[1]; s.msx = d->mask_stride[2];
+    s.vertex = vertex;
+    for (int i = 0; i < 5; ++i) s.vs[i] = d->vertex_stride[i];
+    s.selection = selection;
+    s.B = d->B; s.H = d->H; s.W = d->W; s.K = d->K; s.nwords = L.nwords; s.cap = L.capacity;
+    s.min_num = d->min_num; s.max_num = d->max_num; s.img_base = d->img_base;
+    s.seed = d->seed; s.tag_sel = d->rng_tag_sel ? (uint32_t)d->rng_tag_sel : tag_sel;
+    s.bits = reinterpret_cast<uint32_t *>(w + L.bits);
+    s.wordoff = reinterpret_cast<int *>(w + L.wordoff);
+    s.fgsum = reinterpret_cast<unsigned long long *>(w + L.fgsum);
+    s.nz = reinterpret_cast<int *>(w + L.nz);
+    s.tn = reinterpret_cast<int *>(w + L.tn);
+    s.state = reinterpret_cast<int *>(w + L.state);
+    s.status = reinterpret_cast<int *>(w + L.status);
+    s.xy = reinterpret_cast<float2 *>(w + L.xy);
+    s.dirs = reinterpret_cast<float2 *>(w + L.dirs);
+    VoteArgs &v = P->v;
+    v.B = d->B; v.K = d->K; v.hn = d->hn; v.cap = L.capacity; v.W = d->W; v.H = d->H;
+    v.thresh = d->inlier_thresh;
+    v.tn = s.tn; v.state = s.state; v.xy = s.xy; v.cmax_dev = nullptr; v.ox = 0.f; v.oy = 0.f;
+    v.dirs = s.dirs; v.idxs = idxs; v.seed = d->seed;
+    v.tag_idx = d->rng_tag_idx ? (uint32_t)d->rng_tag_idx : tag_idx;
+    v.img_base = d->img_base;
+    v.hyp = reinterpret_cast<float2 *>(w + L.hyp);
+    v.counts = reinterpret_cast<int *>(w + L.counts);
+    P->win = reinterpret_cast<float2 *>(w + L.win);
+    return PVB_OK;
+}
+
+int run_front(const Plan &P, cudaStream_t st)
+{
+    // status, fgsum, nz are contiguous at the start of the workspace
+    cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.tn, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset(header)");
+    e = launch_select(P.s, st);
+    if (e != cudaSuccess) return cuda_fail(e, "select kernels");
+    e = launch_generate(P.v, st);
+    if (e != cudaSuccess) return cuda_fail(e, "generate kernel");
+    e = launch_vote(P.v, st);
+    if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
+    return PVB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int pvb_version(void) { return PVB_VERSION; }
+const char *pvb_last_error(void) { return g_err; }
+
+size_t pvb_workspace_bytes(const pvb_desc *d)
+{
+    pvb_layout L;
+    if (make_layout(d, &L)) return 0;
+    return L.total;
+}
+
+int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out)
+{
+    if (!out) return fail(PVB_ERR_INVALID, "out is NULL");
+    return make_layout(d, out);
+}
+
+int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
+                         const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
+                         pvb_stream_t stream)
+{
+    Plan P;
+    int rc = make_plan(d, mask, vertex, idxs, selection, workspace, workspace_bytes, 1u, 2u, &P);
+    if (rc) return rc;
+    if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
+    if (d->B == 0) return PVB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = run_front(P, st);
+    if (rc) return rc;
+    cudaError_t e = launch_refit(P.v, P.win, out_kpt, st);
+    if (e != cudaSuccess) return cuda_fail(e, "refit kernel");
+    return PVB_OK;
+}
+
+int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
+                                     const int32_t *idxs, const float *selection, float *out_cov, void *workspace,
+                                     size_t workspace_bytes, pvb_stream_t stream)
+{
+    Plan P;
+    int rc = make_plan(d, mask, vertex, idxs, selection, workspace, workspace_bytes, 3u, 4u, &P);
+    if (rc) return rc;
+    if (!mean || !out_cov) return fail(PVB_ERR_INVALID, "mean/out_cov is NULL");
+    if (d->B == 0) return PVB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = run_front(P, st);
+    if (rc) return rc;
+    cudaError_t e = launch_covariance(P.v, mean, out_cov, st);
+    if (e != cudaSuccess) return cuda_fail(e, "covariance kernel");
+    return PVB_OK;
+}
+
+int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream)
+{
+    pvb_layout L;
+    int rc = make_layout(d, &L);
+    if (rc) return rc;
+    if (!workspace) return fail(PVB_ERR_INVALID, "workspace is NULL");
+    int host[4] = {0, 0, 0, 0};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(host, static_cast<const char *>(workspace) + L.status, sizeof(host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "read status");
+    if (host[0] == PVB_ERR_CAPACITY)
+        return fail(PVB_ERR_CAPACITY, "image %d selected more than capacity=%d pixels; pass capacity=H*W", host[1], L.capacity);
+    if (host[0]) return fail(host[0], "device status %d", host[0]);
+    return PVB_OK;
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------
+static size_t mask_elt_bytes(int dt)
+{
+    switch (dt) {
+    case PVB_MASK_U8: case PVB_MASK_I8: return 1;
+    case PVB_MASK_I16: return 2;
+    case PVB_MASK_I32: case PVB_MASK_F32: return 4;
+    default: return 8;
+    }
+}
+
+struct HostSlot { size_t mask, vertex, out, ws, end; };
+
+static int host_slot_layout(const pvb_desc *d, int chunk, HostSlot *S, pvb_desc *dc)
+{
+    if (chunk <= 0) return fail(PVB_ERR_INVALID, "chunk_images must be > 0");
+    *dc = *d;
+    dc->B = chunk;
+    const size_t HW = (size_t)d->H * d->W;
+    dc->mask_stride[0] = (int64_t)HW; dc->mask_stride[1] = d->W; dc->mask_stride[2] = 1;
+    dc->vertex_stride[0] = (int64_t)(HW * d->K * 2); dc->vertex_stride[1] = (int64_t)d->W * d->K * 2;
+    dc->vertex_stride[2] = (int64_t)d->K * 2; dc->vertex_stride[3] = 2; dc->vertex_stride[4] = 1;
+    pvb_layout L;
+    int rc = make_layout(dc, &L);
+    if (rc) return rc;
+    size_t off = 0;
+    S->mask = off; off = align_up(off + (size_t)chunk * HW * mask_elt_bytes(d->mask_dtype));
+    S->vertex = off; off = align_up(off + (size_t)chunk * HW * d->K * 2 * sizeof(float));
+    S->out = off; off = align_up(off + (size_t)chunk * d->K * 2 * sizeof(float));
+    S->ws = off; off = align_up(off + L.total);
+    S->end = off;
+    return PVB_OK;
+}
+
+size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images)
+{
+    HostSlot S; pvb_desc dc;
+    if (check_desc(d) || host_slot_layout(d, chunk_images, &S, &dc)) return 0;
+    return 2 * S.end;
+}
+
+int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
+                              float *out_kpt_host, int32_t chunk_images, void *dev_scratch, size_t dev_scratch_bytes)
+{
+    int rc = check_desc(d);
+    if (rc) return rc;
+    if (!mask_host || !vertex_host || !out_kpt_host) return fail(PVB_ERR_INVALID, "host buffer is NULL");
+    HostSlot S; pvb_desc dc;
+    rc = host_slot_layout(d, chunk_images, &S, &dc);
+    if (rc) return rc;
+    if (!dev_scratch || dev_scratch_bytes < 2 * S.end) return fail(PVB_ERR_WORKSPACE, "device scratch too small: need %zu", 2 * S.end);
+    if (reinterpret_cast<uintptr_t>(dev_scratch) & 255u) return fail(PVB_ERR_WORKSPACE, "device scratch must be 256-byte aligned");
+    static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
+    static thread_local int streams_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (streams_dev != dev) {
+        for (int i = 0; i < 2; ++i) {
+            e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        }
+        streams_dev = dev;
+    }
+    const size_t HW = (size_t)d->H * d->W;
+    const size_t mbytes = HW * mask_elt_bytes(d->mask_dtype), vbytes = HW * d->K * 2 * sizeof(float);
+    const size_t obytes = (size_t)d->K * 2 * sizeof(float);
+    char *base = static_cast<char *>(dev_scratch);
+    int slot = 0;
+    for (int b0 = 0; b0 < d->B; b0 += chunk_images, slot ^= 1) {
+        const int c = (d->B - b0 < chunk_images) ? d->B - b0 : chunk_images;
+        char *sb = base + (size_t)slot * S.end;
+        cudaStream_t st = streams[slot];
+        e = cudaMemcpyAsync(sb + S.mask, static_cast<const char *>(mask_host) + (size_t)b0 * mbytes, (size_t)c * mbytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(sb + S.vertex, reinterpret_cast<const char *>(vertex_host) + (size_t)b0 * vbytes, (size_t)c * vbytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+        pvb_desc di = dc;
+        di.B = c;
+        di.img_base = d->img_base + b0;
+        pvb_layout L;
+        make_layout(&dc, &L);
+        di.capacity = L.capacity;
+        rc = pvb_ransac_voting_v3(&di, sb + S.mask, reinterpret_cast<const float *>(sb + S.vertex), nullptr, nullptr,
+                                  reinterpret_cast<float *>(sb + S.out), sb + S.ws, S.end - S.ws, st);
+        if (rc) return rc;
+        e = cudaMemcpyAsync(reinterpret_cast<char *>(out_kpt_host) + (size_t)b0 * obytes, sb + S.out, (size_t)c * obytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
+    }
+    for (int i = 0; i < 2; ++i) {
+        e = cudaStreamSynchronize(streams[i]);
+        if (e != cudaSuccess) return cuda_fail(e, "stream sync");
+    }
+    return PVB_OK;
+}
+
+// ---- twins of the reference extension --------------------------------------------------
+static int check_compat(const void *a, const void *b, const void *c, const void *d_, int tn, int vn, int hn)
+{
+    if (tn < 0 || vn < 0 || hn < 0) return fail(PVB_ERR_INVALID, "negative size");
+    if ((long long)hn * vn > (1ll << 30) || (long long)tn * vn > (1ll << 30)) return fail(PVB_ERR_INVALID, "problem too large");
+    if (((tn && vn) && (!a || !b)) || ((hn && vn) && (!c || !d_))) return fail(PVB_ERR_INVALID, "NULL tensor");
+    if (vn > 65535) return fail(PVB_ERR_INVALID, "vn must be <= 65535");
+    return PVB_OK;
+}
+
+int pvb_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hyp, int32_t tn,
+                            int32_t vn, int32_t hn, pvb_stream_t stream)
+{
+    int rc = check_compat(direct, coords, idxs, hyp, tn, vn, hn);
+    if (rc) return rc;
+    cudaError_t e = launch_compat_generate(direct, coords, idxs, hyp, tn, vn, hn, false, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "generate_hypothesis");
+}
+
+int pvb_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
+                                            int32_t tn, int32_t vn, int32_t hn, pvb_stream_t stream)
+{
+    int rc = check_compat(direct, coords, idxs, hyp, tn, vn, hn);
+    if (rc) return rc;
+    cudaError_t e = launch_compat_generate(direct, coords, idxs, hyp, tn, vn, hn, true, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "generate_hypothesis_vanishing_point");
+}
+
+int pvb_voting_for_hypothesis(const float *direct, const float *coords, const float *hyp, uint8_t *inliers, int32_t tn,
+                              int32_t vn, int32_t hn, float inlier_thresh, pvb_stream_t stream)
+{
+    int rc = check_compat(direct, coords, hyp, inliers, tn, vn, hn);
+    if (rc) return rc;
+    if (tn && vn && hn && !inliers) return fail(PVB_ERR_INVALID, "NULL tensor");
+    cudaError_t e = launch_compat_vote(direct, coords, hyp, inliers, tn, vn, hn, inlier_thresh, false, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "voting_for_hypothesis");
+}
+
+int pvb_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hyp,
+                                              uint8_t *inliers, int32_t tn, int32_t vn, int32_t hn,
+                                              float inlier_thresh, pvb_stream_t stream)
+{
+    int rc = check_compat(direct, coords, hyp, inliers, tn, vn, hn);
+    if (rc) return rc;
+    if (tn && vn && hn && !inliers) return fail(PVB_ERR_INVALID, "NULL tensor");
+    cudaError_t e = launch_compat_vote(direct, coords, hyp, inliers, tn, vn, hn, inlier_thresh, true, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "voting_for_hypothesis_vanishing_point");
+}
+
+size_t pvb_vote_count_workspace_bytes(int32_t tn, int32_t vn, int32_t hn)
+{
+    if (tn < 0 || vn < 0 || hn < 0) return 0;
+    size_t off = align_up(4 * sizeof(int));
+    off += align_up((size_t)tn * sizeof(float2));
+    off += align_up((size_t)tn * vn * sizeof(float2));
+    off += align_up((size_t)hn * vn * sizeof(float2));
+    off += align_up((size_t)hn * vn * sizeof(int));
+    return off;
+}
+
+int pvb_vote_count(const float *direct, const float *coords, const float *hyp, int32_t *counts, int32_t tn, int32_t vn,
+                   int32_t hn, float inlier_thresh, void *workspace, size_t workspace_bytes, pvb_stream_t stream)
+{
+    int rc = check_compat(direct, coords, hyp, counts, tn, vn, hn);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (hn == 0 || vn == 0) return PVB_OK;
+    if (tn == 0) {
+        cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)hn * vn, st);
+        return e == cudaSuccess ? PVB_OK : cuda_fail(e, "memset");
+    }
+    if ((long long)vn * ((hn + 511) / 512) > 65535) return fail(PVB_ERR_INVALID, "vn*ceil(hn/512) must be <= 65535");
+    const size_t need = pvb_vote_count_workspace_bytes(tn, vn, hn);
+    if (!workspace || workspace_bytes < need) return fail(PVB_ERR_WORKSPACE, "workspace too small: need %zu", need);
+    if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(PVB_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    char *w = static_cast<char *>(workspace);
+    size_t off = 0;
+    int *meta = reinterpret_cast<int *>(w + off); off += align_up(4 * sizeof(int));
+    float2 *xy = reinterpret_cast<float2 *>(w + off); off += align_up((size_t)tn * sizeof(float2));
+    float2 *dirs = reinterpret_cast<float2 *>(w + off); off += align_up((size_t)tn * vn * sizeof(float2));
+    float2 *hyp_k = reinterpret_cast<float2 *>(w + off); off += align_up((size_t)hn * vn * sizeof(float2));
+    int *counts_k = reinterpret_cast<int *>(w + off);
+    cudaError_t e = launch_compat_repack(direct, coords, hyp, tn, vn, hn, dirs, xy, hyp_k, meta, st);
+    if (e != cudaSuccess) return cuda_fail(e, "repack");
+    VoteArgs v;
+    memset(&v, 0, sizeof(v));
+    v.B = 1; v.K = vn; v.hn = hn; v.cap = tn; v.W = 0; v.H = 0; v.thresh = inlier_thresh;
+    v.tn = meta; v.state = meta + 1; v.xy = xy; v.cmax_dev = reinterpret_cast<const float *>(meta + 2);
+    v.ox = 0.f; v.oy = 0.f; v.dirs = dirs; v.idxs = nullptr; v.hyp = hyp_k; v.counts = counts_k;
+    e = launch_vote(v, st);
+    if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
+    e = launch_compat_unpack_counts(counts_k, counts, vn, hn, st);
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "unpack");
+}
+
+} // extern "C"

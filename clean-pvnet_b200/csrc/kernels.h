@@ -1,0 +1,63 @@
+// kernels.h -- internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pvnet_vote_b200.h"
+
+namespace pvb {
+
+struct SelectArgs {
+    const void *mask;
+    int mask_dtype, select_mode;
+    long long msb, msy, msx;      // mask strides (elements)
+    const float *vertex;
+    long long vs[5];              // vertex strides (elements)
+    const float *selection;       // optional [B,H,W]
+    int B, H, W, K, nwords, cap, min_num, max_num, img_base;
+    uint64_t seed;
+    uint32_t tag_sel;
+    uint32_t *bits;
+    int *wordoff;
+    unsigned long long *fgsum;
+    int *nz, *tn, *state, *status;
+    float2 *xy, *dirs;
+};
+cudaError_t launch_select(const SelectArgs &a, cudaStream_t st);
+
+struct VoteArgs {
+    int B, K, hn, cap, W, H;
+    float thresh;
+    const int *tn;        // [B]
+    const int *state;     // [B]
+    const float2 *xy;     // [B][cap]   pixel coordinates (x,y)
+    const float *cmax_dev; // optional device scalar: max |cx-ox|+|cy-oy| (else derived from W,H)
+    float ox, oy;         // fast-path origin
+    const float2 *dirs;   // [B][K][cap]
+    const int32_t *idxs;  // optional [B][hn][K][2]
+    uint64_t seed;
+    uint32_t tag_idx;
+    int img_base;
+    float2 *hyp;          // [B][K][hn]
+    int *counts;          // [B][K][hn]
+};
+// hypotheses for every (image, keypoint): explicit idxs or philox
+cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st);
+// counts[b][k][h] = #pixels voting for hyp[b][k][h]   (zeroes counts itself)
+cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st);
+// argmax + winner refit -> out_kpt [B][K][2], win [B][K]
+cudaError_t launch_refit(const VoteArgs &a, float2 *win, float *out_kpt, cudaStream_t st);
+// ratio/threshold/weighted covariance -> out_cov [B][K][2][2]
+cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, cudaStream_t st);
+
+// twins of the reference extension on its own layouts
+cudaError_t launch_compat_generate(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
+                                   int tn, int vn, int hn, bool vanishing, cudaStream_t st);
+cudaError_t launch_compat_vote(const float *direct, const float *coords, const float *hyp, uint8_t *inliers,
+                               int tn, int vn, int hn, float thresh, bool vanishing, cudaStream_t st);
+// reference layout -> layer layout (pix/dirs/hyp in k-major) for pvb_vote_count
+// meta: int[4] = { tn, state(0), float bits of max(|cx|+|cy|), unused }
+cudaError_t launch_compat_repack(const float *direct, const float *coords, const float *hyp, int tn, int vn,
+                                 int hn, float2 *dirs, float2 *xy, float2 *hyp_k, int *meta, cudaStream_t st);
+cudaError_t launch_compat_unpack_counts(const int *counts_k, int *counts, int vn, int hn, cudaStream_t st);
+
+} // namespace pvb

@@ -1,0 +1,176 @@
+/*
+ * pvnet_vote_b200.h -- C ABI of the B200-native RANSAC voting layer.
+ *
+ * Drop-in boundary for clean-pvnet's `lib/csrc/ransac_voting` (reference paths
+ * below are relative to the clean-pvnet checkout):
+ *
+ *   reference interface                                         replaced by
+ *   ----------------------------------------------------------  ---------------------------------
+ *   ransac_voting_gpu.py:112  ransac_voting_layer_v3(...)        pvb_ransac_voting_v3
+ *   ransac_voting_gpu.py:6    ransac_voting_layer(...)           pvb_ransac_voting_v3 (same result,
+ *                                                                 see DESIGN.md "v1 vs v3")
+ *   ransac_voting_gpu.py:202  estimate_voting_distribution_...   pvb_estimate_voting_distribution
+ *   src/ransac_voting.cpp:20  generate_hypothesis                pvb_generate_hypothesis
+ *   src/ransac_voting.cpp:41  voting_for_hypothesis              pvb_voting_for_hypothesis
+ *   src/ransac_voting.cpp:64  generate_hypothesis_vanishing_pt   pvb_generate_hypothesis_vanishing_point
+ *   src/ransac_voting.cpp:85  voting_for_hypothesis_vanishing_pt pvb_voting_for_hypothesis_vanishing_point
+ *
+ * Conventions
+ *   - plain C: device pointers, sizes, strides (in ELEMENTS), a CUDA stream
+ *     handle.  No torch types.  All work is enqueued on `stream`; no entry
+ *     point synchronises or allocates (the caller owns the workspace), so the
+ *     calls are CUDA-graph capturable.  Exception: the *_host variants, which
+ *     take HOST buffers and run their own copy/compute pipeline.
+ *   - every function returns PVB_OK (0) or a pvb_status error code;
+ *     pvb_last_error() returns a thread-local description.  Nothing calls
+ *     exit()/abort() (the reference's gpuErrchk does, cuda_common.h:19-25).
+ *   - there is NO CPU implementation behind this ABI.  If no CUDA device is
+ *     usable the calls fail with PVB_ERR_CUDA.
+ */
+#ifndef PVNET_VOTE_B200_H_
+#define PVNET_VOTE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVB_VERSION 100
+
+typedef void *pvb_stream_t; /* cudaStream_t / CUstream, 0 = legacy default stream */
+
+typedef enum pvb_status {
+    PVB_OK = 0,
+    PVB_ERR_INVALID = 1,   /* bad argument (null pointer, shape, dtype, stride) */
+    PVB_ERR_CUDA = 2,      /* CUDA runtime / launch failure, or no usable device */
+    PVB_ERR_WORKSPACE = 3, /* workspace too small or misaligned */
+    PVB_ERR_CAPACITY = 4   /* more pixels selected than `capacity` (reported by pvb_read_status) */
+} pvb_status;
+
+/* element type of the mask tensor (reference: any dtype goes through .byte(), ransac_voting_gpu.py:125) */
+typedef enum pvb_mask_dtype {
+    PVB_MASK_U8 = 0, /* also torch.bool */
+    PVB_MASK_I8 = 1,
+    PVB_MASK_I16 = 2,
+    PVB_MASK_I32 = 3,
+    PVB_MASK_I64 = 4, /* torch.argmax output, resnet18.py:69 */
+    PVB_MASK_F32 = 5,
+    PVB_MASK_F64 = 6
+} pvb_mask_dtype;
+
+/* how foreground pixels are picked */
+typedef enum pvb_select_mode {
+    PVB_SELECT_BYTE = 0, /* v3: (uint8)mask != 0, fg = sum of byte values   (ransac_voting_gpu.py:125-126) */
+    PVB_SELECT_EQ1 = 1   /* distribution: mask == 1, fg = pixel count       (ransac_voting_gpu.py:207-208) */
+} pvb_select_mode;
+
+/* Problem descriptor shared by the layer-level entry points. */
+typedef struct pvb_desc {
+    int32_t B, H, W, K;       /* batch, image height/width, keypoints (vn) */
+    int32_t hn;               /* hypotheses per (image, keypoint): round_hyp_num for v3,
+                                 round_hyp_num*ceil(min_hyp_num/round_hyp_num) for the distribution */
+    float inlier_thresh;      /* cos threshold, compared as fp32 like the reference (.cu:124) */
+    int32_t min_num, max_num; /* ransac_voting_gpu.py:129,135 */
+    int32_t mask_dtype;       /* pvb_mask_dtype */
+    int32_t select_mode;      /* pvb_select_mode */
+    int64_t mask_stride[3];   /* strides of mask [B,H,W], elements */
+    int64_t vertex_stride[5]; /* strides of vertex [B,H,W,K,2], elements (any layout, e.g. the permuted
+                                 NCHW view decode_keypoint passes, resnet18.py:66-68) */
+    int32_t capacity;         /* max selected pixels per image held by the workspace; 0 = default
+                                 (min(H*W, max_num + 8*sqrt(max_num) + 64)); H*W is always safe */
+    int32_t img_base;         /* global index of image 0 (multi-GPU shards keep one philox stream) */
+    uint64_t seed;            /* philox seed, used when idxs / selection are NULL */
+    int32_t rng_tag_idx;      /* philox stream tags (see DESIGN.md "Sampling"); 0 = per-op default */
+    int32_t rng_tag_sel;
+} pvb_desc;
+
+/* Offsets (bytes from the workspace base) of the intermediate buffers; for tests and tooling. */
+typedef struct pvb_layout {
+    size_t total;    /* == pvb_workspace_bytes() */
+    size_t status;   /* int32[4]: [0] sticky error code (pvb_status), [1] image that overflowed */
+    size_t fgsum;    /* uint64[B]  sum of mask bytes (BYTE) / count (EQ1) */
+    size_t nz;       /* int32[B]   selected-before-thinning count */
+    size_t tn;       /* int32[B]   selected pixel count after thinning (0 when skipped) */
+    size_t state;    /* int32[B]   0 ok, 1 skipped (fg < min_num) */
+    size_t bits;     /* uint32[B][nwords] selection bitmap, bit j of word w = pixel 32*w+j */
+    size_t wordoff;  /* int32[B][nwords]  exclusive prefix of popcounts */
+    size_t xy;       /* float2[B][capacity]   (x,y) of the t-th selected pixel, row-major (torch.nonzero) order */
+    size_t dirs;     /* float2[B][K][capacity] gathered vertex vectors (k-major) */
+    size_t hyp;      /* float2[B][K][hn] */
+    size_t counts;   /* int32[B][K][hn] */
+    size_t win;      /* float2[B][K] winning hypothesis before the refit */
+    int32_t nwords;  /* ceil(H*W/32) */
+    int32_t capacity;
+} pvb_layout;
+
+int pvb_version(void);
+const char *pvb_last_error(void);
+
+/* Workspace sizing.  The workspace must be 256-byte aligned device memory. */
+size_t pvb_workspace_bytes(const pvb_desc *d);
+int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out);
+
+/* ransac_voting_layer_v3 (ransac_voting_gpu.py:112-199), whole batch, no host sync.
+ *   mask    device, [B,H,W] of d->mask_dtype with d->mask_stride
+ *   vertex  device fp32, [B,H,W,K,2] with d->vertex_stride
+ *   idxs    optional device int32 [B,hn,K,2] contiguous: the reference's per-image `idxs`
+ *           (:145).  NULL -> drawn in-kernel from the philox stream (seed, tag, image, k, h).
+ *   selection optional device fp32 [B,H,W] contiguous: the reference's U(0,1) `selection`
+ *           (:136), consulted only for images with fg > max_num.  NULL -> philox.
+ *   out_kpt device fp32 [B,K,2] contiguous.
+ * `confidence` / `max_iter` of the reference do not influence its result (idxs is drawn once,
+ * outside the loop, :145 vs :150) and therefore have no counterpart here. */
+int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex,
+                         const int32_t *idxs, const float *selection, float *out_kpt,
+                         void *workspace, size_t workspace_bytes, pvb_stream_t stream);
+
+/* estimate_voting_distribution_with_mean (ransac_voting_gpu.py:202-274).
+ *   mean device fp32 [B,K,2];  out_cov device fp32 [B,K,2,2].  d->select_mode must be
+ *   PVB_SELECT_EQ1 to match the reference (:207).  idxs optional int32 [B,hn,K,2] (the 16
+ *   per-round draws of :235 concatenated in round order). */
+int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex,
+                                     const float *mean, const int32_t *idxs, const float *selection,
+                                     float *out_cov, void *workspace, size_t workspace_bytes,
+                                     pvb_stream_t stream);
+
+/* Reads the sticky status word of a workspace (synchronises `stream`). */
+int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream);
+
+/* HOST-buffer variant of pvb_ransac_voting_v3: mask/vertex/out_kpt are host pointers
+ * (pinned for full speed), contiguous [B,H,W] / [B,H,W,K,2] / [B,K,2].  Splits the batch into
+ * `chunk_images`-sized pieces and overlaps H2D copies with compute on two internal streams.
+ * dev_scratch: device memory of pvb_host_scratch_bytes(d, chunk_images) bytes. Synchronous. */
+size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images);
+int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
+                              float *out_kpt_host, int32_t chunk_images,
+                              void *dev_scratch, size_t dev_scratch_bytes);
+
+/* ---- twins of the reference pybind module `ransac_voting` (ransac_voting.cpp:102-107) ---- */
+/* direct [tn,vn,2] f32, coords [tn,2] f32, idxs [hn,vn,2] i32 -> hyp [hn,vn,2] f32 (fully written;
+ * degenerate pairs give (0,0), the reference's zero fill, .cu:42-43,75) */
+int pvb_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
+                            int32_t tn, int32_t vn, int32_t hn, pvb_stream_t stream);
+/* sets inliers[h,k,t]=1 (uint8 [hn,vn,tn]) where the test passes; other bytes untouched (.cu:124-125) */
+int pvb_voting_for_hypothesis(const float *direct, const float *coords, const float *hyp, uint8_t *inliers,
+                              int32_t tn, int32_t vn, int32_t hn, float inlier_thresh, pvb_stream_t stream);
+/* hyp [hn,vn,3] */
+int pvb_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs,
+                                            float *hyp, int32_t tn, int32_t vn, int32_t hn,
+                                            pvb_stream_t stream);
+int pvb_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hyp,
+                                              uint8_t *inliers, int32_t tn, int32_t vn, int32_t hn,
+                                              float inlier_thresh, pvb_stream_t stream);
+
+/* Fused count of the above (voting_for_hypothesis + torch.sum(dim 2), ransac_voting_gpu.py:156-159)
+ * on the reference layouts: counts int32 [hn,vn].  Same kernel the layer uses. */
+int pvb_vote_count(const float *direct, const float *coords, const float *hyp, int32_t *counts,
+                   int32_t tn, int32_t vn, int32_t hn, float inlier_thresh,
+                   void *workspace, size_t workspace_bytes, pvb_stream_t stream);
+size_t pvb_vote_count_workspace_bytes(int32_t tn, int32_t vn, int32_t hn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVNET_VOTE_B200_H_ */

@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- RANSAC-vote throughput (images*keypoints/s) of the B200-native voting layer.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (torchrun for N>1)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's own path
+
+One "step" = one ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99) call over one batch of
+BASELINE.json's configs[1] ("cfg2": B=16, 480x640, K=9, 512 hypotheses, ~30 % mask fill, int64 mask,
+contiguous [B,H,W,K,2] vertex) per GPU; weak scaling (every rank owns a full batch, results
+all_gathered over NCCL inside the step).  Prints ONE JSON line on rank 0.
+
+  value      whole-job images*keypoints/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the host-buffer entry (pinned host inputs -> H2D -> kernels -> D2H)
+  roofline   dominant kernel (vote) : algorithmic bytes of the op / its CUDA-event duration vs measured HBM peak
+  cpu_baseline  the CPU oracle port timed on this box's host cores (bounded sample), rank 0, N=1 only
+
+--impl reference times the UNMODIFIED reference (its CUDA extension compiled for sm_100 by
+oracle/build_ref.py + its own Python operator, loaded from oracle/_ref) on the same tensors; the
+reference has no CPU implementation (ransac_voting.cpp:7-9 asserts CUDA), so where oracle/_ref cannot
+be loaded the CPU oracle port is timed instead and the line says so (cpu_baseline.kind).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT,):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "ransac_vote_throughput"
+UNIT = "images*keypoints/s"
+WORKLOAD = "cfg2"
+HN = 512
+THRESH = 0.99
+KERNELS_PER_STEP = 6   # mask_bits, select_scan, gather, generate, vote, refit
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if not self.samples:
+            return None
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _algorithmic_bytes(B, H, W, K, tn_sum, mask_elt=8):
+    # B*[H*W*sizeof(mask) + tn*K*8 + K*8]  (read each mask element once, the selected
+    # pixels' K vectors once, write K keypoints)
+    return B * H * W * mask_elt + tn_sum * K * 8 + B * K * 8
+
+
+def _cpu_baseline(mask, vertex, K, seconds_target=15.0):
+    """Oracle port (oracle/pvnet_oracle.c) on the host cores: one image per thread at a time."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import pvnet_oracle
+    pvnet_oracle.build()
+    cores = os.cpu_count() or 1
+    m = mask.cpu().numpy().astype(np.int64)
+    v = vertex.cpu().numpy()
+    B = m.shape[0]
+    t0 = time.perf_counter()
+    pvnet_oracle.ransac_voting_layer_v3(m[:1], v[:1], HN, inlier_thresh=THRESH, seed=1)
+    t_one = time.perf_counter() - t0
+    n_img = int(max(1, min(cores * max(1, int(seconds_target / max(t_one, 1e-3))), 4 * cores)))
+    done = [0]
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = done[0]
+                if i >= n_img:
+                    return
+                done[0] += 1
+            b = i % B
+            pvnet_oracle.ransac_voting_layer_v3(m[b:b + 1], v[b:b + 1], HN, inlier_thresh=THRESH, seed=1, img_base=i)
+
+    t0 = time.perf_counter()
+    thr = [threading.Thread(target=work) for _ in range(min(cores, n_img))]
+    for t in thr:
+        t.start()
+    for t in thr:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"value": n_img * K / dt, "unit": UNIT, "cores": min(cores, n_img), "kind": "port",
+            "sample": f"{n_img} images of {WORKLOAD} (480x640, K={K}, hn={HN}) through oracle/pvnet_oracle.c, "
+                      f"{min(cores, n_img)} threads, {dt:.1f} s", "single_image_s": t_one}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import clean_pvnet_b200 as pvb
+    from clean_pvnet_b200 import _lib, parallel, synth
+
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    cfg = synth.CONFIGS[WORKLOAD]
+    B, H, W, K = cfg["B"], cfg["H"], cfg["W"], cfg["K"]
+    mask, vertex, _ = synth.make_inputs(WORKLOAD, device=dev, seed=1234 + 2 + rank, layout=args.layout)
+    total = B * world
+
+    def step(i):
+        local_out = pvb.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH, seed=1000 + i,
+                                               img_base=rank * B)
+        if world > 1:
+            return parallel.all_gather_ragged(local_out, total)
+        return local_out
+
+    # one debug call for the workload's tn (units of algorithmic bytes / tests)
+    _, dbg = pvb.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH, seed=999, img_base=rank * B, debug=True)
+    tn_sum = int(dbg["tn"].sum().item())
+    del dbg
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    lib.pvb_profile_reset()
+    lib.pvb_profile_enable(1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        out = step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    import ctypes
+    stage = (ctypes.c_double * 4)()
+    calls = lib.pvb_profile_read(stage, 4)
+    lib.pvb_profile_enable(0)
+    stage_ms = [stage[i] / max(calls, 1) for i in range(4)]
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = total * K / (ms_per_step * 1e-3)
+
+    # ---- end-to-end: pinned host inputs -> H2D -> kernels -> D2H, through the public host entry
+    mh, vh = mask.cpu().pin_memory(), vertex.contiguous().cpu().pin_memory()
+    oh = torch.empty((B, K, 2), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(3):
+        pvb.ransac_voting_layer_v3_host(mh, vh, HN, inlier_thresh=THRESH, seed=1, img_base=rank * B,
+                                        chunk_images=args.chunk, out=oh, device=dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        pvb.ransac_voting_layer_v3_host(mh, vh, HN, inlier_thresh=THRESH, seed=1000 + i, img_base=rank * B,
+                                        chunk_images=args.chunk, out=oh, device=dev)
+    e1.record()
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item()) / e2e_steps
+    h2d = mh.numel() * mh.element_size() + vh.numel() * vh.element_size()
+    d2h = oh.numel() * oh.element_size()
+
+    if rank == 0:
+        hbm_peak, peak_src = _peaks()
+        bytes_alg = _algorithmic_bytes(B, H, W, K, tn_sum, mask.element_size())
+        vote_ms = stage_ms[2]
+        achieved = bytes_alg / (vote_ms * 1e-3) / 1e9 if vote_ms > 0 else None
+        tests = K * HN * tn_sum
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{WORKLOAD}: B={B}/GPU 480x640 K={K} hn={HN} inlier_thresh={THRESH} fill~30% "
+                            f"{str(mask.dtype).replace('torch.', '')} mask, vertex layout={args.layout}, max_num=30000",
+                "global_batch": total, "selected_pixels_per_image": tn_sum / B,
+                "l2": "inputs larger than L2 (mask+vertex = %.0f MB per GPU > 126 MB); no explicit flush" % (h2d / 1e6),
+                "parallelism": f"dp{world} (images sharded, NCCL all_gather of [B,K,2] in the step)" if world > 1 else "single GPU",
+                "sampling": "philox (in-kernel), new seed every step",
+            },
+            "clocks": clocks,
+            "e2e": {"value": total * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "chunk_images": args.chunk,
+                    "api": "ransac_voting_layer_v3_host -> pvb_ransac_voting_v3_host (pinned host buffers)"},
+            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (achieved / hbm_peak) if achieved else None, "traffic": args.traffic,
+                "kernel": "pvb::vote_kernel<4,128>", "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
+                "peak_source": peak_src,
+                "note": "the vote kernel is FP32-issue bound by construction (hn inlier tests per 16 loaded bytes); "
+                        "see 'alu' and DESIGN.md",
+            },
+            "alu": {"inlier_tests_per_step": tests, "tests_per_s_vote_kernel": tests / (vote_ms * 1e-3) if vote_ms else None,
+                    "lane_ops_peak_per_s": 148 * 128 * sm_mhz * 1e6},
+            "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = _cpu_baseline(mask, vertex, K, args.cpu_seconds)
+            except Exception as e:   # the oracle is a checker; its absence must not hide the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+        sys.stdout.flush()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return          # the reference has no multi-GPU path: rank 0 alone runs it
+    import torch
+    from clean_pvnet_b200 import synth
+    cfg = synth.CONFIGS[WORKLOAD]
+    B, H, W, K = cfg["B"], cfg["H"], cfg["W"], cfg["K"]
+    local = _env_int("LOCAL_RANK", 0)
+    gpu_ref = None
+    if torch.cuda.is_available():
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from refload import load_reference
+            _, gpu_ref = load_reference()
+        except Exception as e:
+            gpu_ref, why = None, str(e)
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": _env_int("WORLD_SIZE", 1), "steps": args.steps,
+            "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference"}
+    if gpu_ref is not None:
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        mask, vertex, _ = synth.make_inputs(WORKLOAD, device=dev, seed=1234 + 2, layout=args.layout)
+        for i in range(max(args.warmup, 3)):
+            torch.manual_seed(i)
+            gpu_ref.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            torch.manual_seed(1000 + i)
+            gpu_ref.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH)
+        ev1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms_per_step = ev0.elapsed_time(ev1) / args.steps
+        value = B * K / (ms_per_step * 1e-3)
+        line = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks,
+                    config={"workload": f"{WORKLOAD}: B={B} 480x640 K={K} hn={HN} inlier_thresh={THRESH} fill~30% int64 mask, "
+                                        f"vertex layout={args.layout}, max_num=30000",
+                            "global_batch": B, "parallelism": "single GPU (the reference has no multi-GPU path)",
+                            "implementation": "unmodified clean-pvnet lib/csrc/ransac_voting (CUDA ext compiled for sm_100 "
+                                              "by oracle/build_ref.py) through its own ransac_voting_layer_v3"},
+                    cpu_baseline={"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                                  "sample": f"{args.steps} full {WORKLOAD} batches on 1 GPU (the reference path is CUDA-only, "
+                                            "ransac_voting.cpp:7-9)"},
+                    e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    else:
+        mask, vertex, _ = synth.make_inputs(WORKLOAD, device="cpu", seed=1234 + 2, B=min(B, 4))
+        cb = _cpu_baseline(mask, vertex, K, args.cpu_seconds)
+        line = dict(base, value=cb["value"], ms_per_step=None,
+                    config={"workload": f"{WORKLOAD} (bounded sample) through the CPU oracle port; reference CUDA "
+                                        "extension not loadable here"},
+                    cpu_baseline=cb, e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                          "d2h_bytes_per_step": 0})
+    print(json.dumps(line))
+    sys.stdout.flush()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="interleaved", choices=["interleaved", "planar"])
+    ap.add_argument("--chunk", type=int, default=2, help="images per H2D chunk of the end-to-end path")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes/launch of the vote kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

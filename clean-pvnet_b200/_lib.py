@@ -47,7 +47,10 @@ SIGNATURES = {
     "pvb_estimate_voting_distribution": (ctypes.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pvb_read_status": (ctypes.c_int, [_dp, _vp, _vp]),
     "pvb_host_scratch_bytes": (_sz, [_dp, _i32]),
-    "pvb_ransac_voting_v3_host": (ctypes.c_int, [_dp, _vp, _vp, _vp, _i32, _vp, _sz]),
+    "pvb_ransac_voting_v3_host": (ctypes.c_int, [_dp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "pvb_profile_enable": (ctypes.c_int, [_i32]),
+    "pvb_profile_reset": (ctypes.c_int, []),
+    "pvb_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), _i32]),
     "pvb_generate_hypothesis": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pvb_voting_for_hypothesis": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _vp]),
     "pvb_generate_hypothesis_vanishing_point": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "kernels.h"
 
 using namespace pvb;
@@ -26,6 +27,35 @@ int cuda_fail(cudaError_t e, const char *what)
 }
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// ---- stage timing (pvb_profile_*) --------------------------------------------------------
+struct ProfCall { cudaEvent_t ev[PVB_STAGE_COUNT + 1]; };
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfCall> g_prof_calls;
+thread_local std::vector<cudaEvent_t> g_prof_pool;
+
+cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfCall *prof_begin(cudaStream_t st)
+{
+    if (!g_prof_on) return nullptr;
+    ProfCall pc;
+    for (auto &e : pc.ev) e = prof_event();
+    g_prof_calls.push_back(pc);
+    cudaEventRecord(g_prof_calls.back().ev[0], st);
+    return &g_prof_calls.back();
+}
+
+inline void prof_mark(ProfCall *pc, int stage, cudaStream_t st)
+{
+    if (pc) cudaEventRecord(pc->ev[stage + 1], st);
+}
 
 int default_capacity(const pvb_desc *d)
 {
@@ -129,17 +159,20 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     return PVB_OK;
 }
 
-int run_front(const Plan &P, cudaStream_t st)
+int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
 {
     // status, fgsum, nz are contiguous at the start of the workspace
     cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.tn, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(header)");
     e = launch_select(P.s, st);
     if (e != cudaSuccess) return cuda_fail(e, "select kernels");
+    prof_mark(pc, PVB_STAGE_SELECT, st);
     e = launch_generate(P.v, st);
     if (e != cudaSuccess) return cuda_fail(e, "generate kernel");
+    prof_mark(pc, PVB_STAGE_GENERATE, st);
     e = launch_vote(P.v, st);
     if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
+    prof_mark(pc, PVB_STAGE_VOTE, st);
     return PVB_OK;
 }
 
@@ -147,23 +180,23 @@ int run_front(const Plan &P, cudaStream_t st)
 
 extern "C" {
 
-int pvb_version(void) { return PVB_VERSION; }
-const char *pvb_last_error(void) { return g_err; }
+PVB_API int pvb_version(void) { return PVB_VERSION; }
+PVB_API const char *pvb_last_error(void) { return g_err; }
 
-size_t pvb_workspace_bytes(const pvb_desc *d)
+PVB_API size_t pvb_workspace_bytes(const pvb_desc *d)
 {
     pvb_layout L;
     if (make_layout(d, &L)) return 0;
     return L.total;
 }
 
-int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out)
+PVB_API int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out)
 {
     if (!out) return fail(PVB_ERR_INVALID, "out is NULL");
     return make_layout(d, out);
 }
 
-int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
+PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
                          const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
                          pvb_stream_t stream)
 {
@@ -173,14 +206,16 @@ int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *verte
     if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
     if (d->B == 0) return PVB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = run_front(P, st);
+    ProfCall *pc = prof_begin(st);
+    rc = run_front(P, st, pc);
     if (rc) return rc;
     cudaError_t e = launch_refit(P.v, P.win, out_kpt, st);
     if (e != cudaSuccess) return cuda_fail(e, "refit kernel");
+    prof_mark(pc, PVB_STAGE_FINISH, st);
     return PVB_OK;
 }
 
-int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
+PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
                                      const int32_t *idxs, const float *selection, float *out_cov, void *workspace,
                                      size_t workspace_bytes, pvb_stream_t stream)
 {
@@ -190,14 +225,16 @@ int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const 
     if (!mean || !out_cov) return fail(PVB_ERR_INVALID, "mean/out_cov is NULL");
     if (d->B == 0) return PVB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = run_front(P, st);
+    ProfCall *pc = prof_begin(st);
+    rc = run_front(P, st, pc);
     if (rc) return rc;
     cudaError_t e = launch_covariance(P.v, mean, out_cov, st);
     if (e != cudaSuccess) return cuda_fail(e, "covariance kernel");
+    prof_mark(pc, PVB_STAGE_FINISH, st);
     return PVB_OK;
 }
 
-int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream)
+PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream)
 {
     pvb_layout L;
     int rc = make_layout(d, &L);
@@ -248,15 +285,16 @@ static int host_slot_layout(const pvb_desc *d, int chunk, HostSlot *S, pvb_desc 
     return PVB_OK;
 }
 
-size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images)
+PVB_API size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images)
 {
     HostSlot S; pvb_desc dc;
     if (check_desc(d) || host_slot_layout(d, chunk_images, &S, &dc)) return 0;
     return 2 * S.end;
 }
 
-int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
-                              float *out_kpt_host, int32_t chunk_images, void *dev_scratch, size_t dev_scratch_bytes)
+PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
+                              float *out_kpt_host, int32_t chunk_images, void *dev_scratch, size_t dev_scratch_bytes,
+                              pvb_stream_t stream)
 {
     int rc = check_desc(d);
     if (rc) return rc;
@@ -267,6 +305,7 @@ int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const fl
     if (!dev_scratch || dev_scratch_bytes < 2 * S.end) return fail(PVB_ERR_WORKSPACE, "device scratch too small: need %zu", 2 * S.end);
     if (reinterpret_cast<uintptr_t>(dev_scratch) & 255u) return fail(PVB_ERR_WORKSPACE, "device scratch must be 256-byte aligned");
     static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
+    static thread_local cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     static thread_local int streams_dev = -1;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -276,12 +315,26 @@ int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const fl
             e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking);
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
         }
+        for (int i = 0; i < 3; ++i) {
+            e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        }
         streams_dev = dev;
+    }
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    e = cudaEventRecord(ev[2], user);
+    if (e != cudaSuccess) return cuda_fail(e, "event record");
+    for (int i = 0; i < 2; ++i) {
+        e = cudaStreamWaitEvent(streams[i], ev[2], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "stream wait");
     }
     const size_t HW = (size_t)d->H * d->W;
     const size_t mbytes = HW * mask_elt_bytes(d->mask_dtype), vbytes = HW * d->K * 2 * sizeof(float);
     const size_t obytes = (size_t)d->K * 2 * sizeof(float);
     char *base = static_cast<char *>(dev_scratch);
+    pvb_layout Lc;
+    rc = make_layout(&dc, &Lc);
+    if (rc) return rc;
     int slot = 0;
     for (int b0 = 0; b0 < d->B; b0 += chunk_images, slot ^= 1) {
         const int c = (d->B - b0 < chunk_images) ? d->B - b0 : chunk_images;
@@ -294,9 +347,7 @@ int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const fl
         pvb_desc di = dc;
         di.B = c;
         di.img_base = d->img_base + b0;
-        pvb_layout L;
-        make_layout(&dc, &L);
-        di.capacity = L.capacity;
+        di.capacity = Lc.capacity;
         rc = pvb_ransac_voting_v3(&di, sb + S.mask, reinterpret_cast<const float *>(sb + S.vertex), nullptr, nullptr,
                                   reinterpret_cast<float *>(sb + S.out), sb + S.ws, S.end - S.ws, st);
         if (rc) return rc;
@@ -304,10 +355,42 @@ int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const fl
         if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
     }
     for (int i = 0; i < 2; ++i) {
-        e = cudaStreamSynchronize(streams[i]);
-        if (e != cudaSuccess) return cuda_fail(e, "stream sync");
+        e = cudaEventRecord(ev[i], streams[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ev[i], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "join streams");
     }
+    e = cudaStreamSynchronize(user);
+    if (e != cudaSuccess) return cuda_fail(e, "stream sync");
     return PVB_OK;
+}
+
+PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK; }
+
+PVB_API int pvb_profile_reset(void)
+{
+    for (auto &pc : g_prof_calls)
+        for (auto e : pc.ev) g_prof_pool.push_back(e);
+    g_prof_calls.clear();
+    return PVB_OK;
+}
+
+PVB_API int pvb_profile_read(double *ms, int32_t n)
+{
+    if (!ms || n < PVB_STAGE_COUNT) return fail(PVB_ERR_INVALID, "ms must hold PVB_STAGE_COUNT doubles");
+    int calls = 0;
+    for (auto &pc : g_prof_calls) {
+        cudaError_t e = cudaEventSynchronize(pc.ev[PVB_STAGE_COUNT]);
+        if (e != cudaSuccess) { cuda_fail(e, "profile event sync"); return -1; }
+        for (int i = 0; i < PVB_STAGE_COUNT; ++i) {
+            float t = 0.f;
+            e = cudaEventElapsedTime(&t, pc.ev[i], pc.ev[i + 1]);
+            if (e != cudaSuccess) { cuda_fail(e, "profile elapsed"); return -1; }
+            ms[i] += (double)t;
+        }
+        ++calls;
+    }
+    pvb_profile_reset();
+    return calls;
 }
 
 // ---- twins of the reference extension --------------------------------------------------
@@ -320,7 +403,7 @@ static int check_compat(const void *a, const void *b, const void *c, const void 
     return PVB_OK;
 }
 
-int pvb_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hyp, int32_t tn,
+PVB_API int pvb_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hyp, int32_t tn,
                             int32_t vn, int32_t hn, pvb_stream_t stream)
 {
     int rc = check_compat(direct, coords, idxs, hyp, tn, vn, hn);
@@ -329,7 +412,7 @@ int pvb_generate_hypothesis(const float *direct, const float *coords, const int3
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "generate_hypothesis");
 }
 
-int pvb_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
+PVB_API int pvb_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
                                             int32_t tn, int32_t vn, int32_t hn, pvb_stream_t stream)
 {
     int rc = check_compat(direct, coords, idxs, hyp, tn, vn, hn);
@@ -338,7 +421,7 @@ int pvb_generate_hypothesis_vanishing_point(const float *direct, const float *co
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "generate_hypothesis_vanishing_point");
 }
 
-int pvb_voting_for_hypothesis(const float *direct, const float *coords, const float *hyp, uint8_t *inliers, int32_t tn,
+PVB_API int pvb_voting_for_hypothesis(const float *direct, const float *coords, const float *hyp, uint8_t *inliers, int32_t tn,
                               int32_t vn, int32_t hn, float inlier_thresh, pvb_stream_t stream)
 {
     int rc = check_compat(direct, coords, hyp, inliers, tn, vn, hn);
@@ -348,7 +431,7 @@ int pvb_voting_for_hypothesis(const float *direct, const float *coords, const fl
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "voting_for_hypothesis");
 }
 
-int pvb_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hyp,
+PVB_API int pvb_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hyp,
                                               uint8_t *inliers, int32_t tn, int32_t vn, int32_t hn,
                                               float inlier_thresh, pvb_stream_t stream)
 {
@@ -359,7 +442,7 @@ int pvb_voting_for_hypothesis_vanishing_point(const float *direct, const float *
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "voting_for_hypothesis_vanishing_point");
 }
 
-size_t pvb_vote_count_workspace_bytes(int32_t tn, int32_t vn, int32_t hn)
+PVB_API size_t pvb_vote_count_workspace_bytes(int32_t tn, int32_t vn, int32_t hn)
 {
     if (tn < 0 || vn < 0 || hn < 0) return 0;
     size_t off = align_up(4 * sizeof(int));
@@ -370,7 +453,7 @@ size_t pvb_vote_count_workspace_bytes(int32_t tn, int32_t vn, int32_t hn)
     return off;
 }
 
-int pvb_vote_count(const float *direct, const float *coords, const float *hyp, int32_t *counts, int32_t tn, int32_t vn,
+PVB_API int pvb_vote_count(const float *direct, const float *coords, const float *hyp, int32_t *counts, int32_t tn, int32_t vn,
                    int32_t hn, float inlier_thresh, void *workspace, size_t workspace_bytes, pvb_stream_t stream)
 {
     int rc = check_compat(direct, coords, hyp, counts, tn, vn, hn);

@@ -296,7 +296,8 @@ def ransac_voting_layer_v3_host(mask, vertex, round_hyp_num, inlier_thresh=0.999
             sc = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             _host_scratch[key] = sc
         _lib.check(lib.pvb_ransac_voting_v3_host(d, mask.data_ptr(), vertex.data_ptr(), out.data_ptr(), chunk,
-                                                 sc.data_ptr(), sc.numel()))
+                                                 sc.data_ptr(), sc.numel(),
+                                                 torch.cuda.current_stream(dev).cuda_stream))
     return out
 
 

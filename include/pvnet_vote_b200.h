@@ -39,6 +39,12 @@ extern "C" {
 
 #define PVB_VERSION 100
 
+#if defined(__GNUC__)
+#define PVB_API __attribute__((visibility("default")))
+#else
+#define PVB_API
+#endif
+
 typedef void *pvb_stream_t; /* cudaStream_t / CUstream, 0 = legacy default stream */
 
 typedef enum pvb_status {
@@ -105,12 +111,12 @@ typedef struct pvb_layout {
     int32_t capacity;
 } pvb_layout;
 
-int pvb_version(void);
-const char *pvb_last_error(void);
+PVB_API int pvb_version(void);
+PVB_API const char *pvb_last_error(void);
 
 /* Workspace sizing.  The workspace must be 256-byte aligned device memory. */
-size_t pvb_workspace_bytes(const pvb_desc *d);
-int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out);
+PVB_API size_t pvb_workspace_bytes(const pvb_desc *d);
+PVB_API int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out);
 
 /* ransac_voting_layer_v3 (ransac_voting_gpu.py:112-199), whole batch, no host sync.
  *   mask    device, [B,H,W] of d->mask_dtype with d->mask_stride
@@ -122,7 +128,7 @@ int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out);
  *   out_kpt device fp32 [B,K,2] contiguous.
  * `confidence` / `max_iter` of the reference do not influence its result (idxs is drawn once,
  * outside the loop, :145 vs :150) and therefore have no counterpart here. */
-int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex,
+PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex,
                          const int32_t *idxs, const float *selection, float *out_kpt,
                          void *workspace, size_t workspace_bytes, pvb_stream_t stream);
 
@@ -130,45 +136,61 @@ int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *verte
  *   mean device fp32 [B,K,2];  out_cov device fp32 [B,K,2,2].  d->select_mode must be
  *   PVB_SELECT_EQ1 to match the reference (:207).  idxs optional int32 [B,hn,K,2] (the 16
  *   per-round draws of :235 concatenated in round order). */
-int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex,
+PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex,
                                      const float *mean, const int32_t *idxs, const float *selection,
                                      float *out_cov, void *workspace, size_t workspace_bytes,
                                      pvb_stream_t stream);
 
 /* Reads the sticky status word of a workspace (synchronises `stream`). */
-int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream);
+PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream);
 
 /* HOST-buffer variant of pvb_ransac_voting_v3: mask/vertex/out_kpt are host pointers
  * (pinned for full speed), contiguous [B,H,W] / [B,H,W,K,2] / [B,K,2].  Splits the batch into
- * `chunk_images`-sized pieces and overlaps H2D copies with compute on two internal streams.
- * dev_scratch: device memory of pvb_host_scratch_bytes(d, chunk_images) bytes. Synchronous. */
-size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images);
-int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
+ * `chunk_images`-sized pieces and overlaps the H2D copies with compute on two internal streams.
+ * Stream-ordered after the work already queued on `stream`; `stream` is synchronised before the
+ * call returns (the result is in host memory), so CUDA events recorded on `stream` around the call
+ * bracket all copies and kernels.  dev_scratch: 256-byte aligned device memory of
+ * pvb_host_scratch_bytes(d, chunk_images) bytes. */
+PVB_API size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images);
+PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
                               float *out_kpt_host, int32_t chunk_images,
-                              void *dev_scratch, size_t dev_scratch_bytes);
+                              void *dev_scratch, size_t dev_scratch_bytes, pvb_stream_t stream);
+
+/* Stage timing (tooling, used by bench.py).  When enabled, the layer entry points record CUDA
+ * events on the launching stream around each stage; pvb_profile_read() synchronises those events
+ * and ADDS the elapsed milliseconds of every call since the last pvb_profile_reset() into
+ * ms[PVB_STAGE_COUNT], returning the number of calls accumulated.  Per host thread. */
+enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
+       PVB_STAGE_GENERATE = 1, /* hypothesis generation */
+       PVB_STAGE_VOTE = 2,     /* counts memset + vote kernel (the dominant kernel) */
+       PVB_STAGE_FINISH = 3,   /* winner + refit, or covariance */
+       PVB_STAGE_COUNT = 4 };
+PVB_API int pvb_profile_enable(int32_t on);
+PVB_API int pvb_profile_reset(void);
+PVB_API int pvb_profile_read(double *ms, int32_t n);
 
 /* ---- twins of the reference pybind module `ransac_voting` (ransac_voting.cpp:102-107) ---- */
 /* direct [tn,vn,2] f32, coords [tn,2] f32, idxs [hn,vn,2] i32 -> hyp [hn,vn,2] f32 (fully written;
  * degenerate pairs give (0,0), the reference's zero fill, .cu:42-43,75) */
-int pvb_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
+PVB_API int pvb_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
                             int32_t tn, int32_t vn, int32_t hn, pvb_stream_t stream);
 /* sets inliers[h,k,t]=1 (uint8 [hn,vn,tn]) where the test passes; other bytes untouched (.cu:124-125) */
-int pvb_voting_for_hypothesis(const float *direct, const float *coords, const float *hyp, uint8_t *inliers,
+PVB_API int pvb_voting_for_hypothesis(const float *direct, const float *coords, const float *hyp, uint8_t *inliers,
                               int32_t tn, int32_t vn, int32_t hn, float inlier_thresh, pvb_stream_t stream);
 /* hyp [hn,vn,3] */
-int pvb_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs,
+PVB_API int pvb_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs,
                                             float *hyp, int32_t tn, int32_t vn, int32_t hn,
                                             pvb_stream_t stream);
-int pvb_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hyp,
+PVB_API int pvb_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hyp,
                                               uint8_t *inliers, int32_t tn, int32_t vn, int32_t hn,
                                               float inlier_thresh, pvb_stream_t stream);
 
 /* Fused count of the above (voting_for_hypothesis + torch.sum(dim 2), ransac_voting_gpu.py:156-159)
  * on the reference layouts: counts int32 [hn,vn].  Same kernel the layer uses. */
-int pvb_vote_count(const float *direct, const float *coords, const float *hyp, int32_t *counts,
+PVB_API int pvb_vote_count(const float *direct, const float *coords, const float *hyp, int32_t *counts,
                    int32_t tn, int32_t vn, int32_t hn, float inlier_thresh,
                    void *workspace, size_t workspace_bytes, pvb_stream_t stream);
-size_t pvb_vote_count_workspace_bytes(int32_t tn, int32_t vn, int32_t hn);
+PVB_API size_t pvb_vote_count_workspace_bytes(int32_t tn, int32_t vn, int32_t hn);
 
 #ifdef __cplusplus
 }

@@ -16,8 +16,9 @@ travels to the GPU box with gpurun):
        * src/ransac_voting.cpp:5   `extern THCState* state;`  (unused; THC is gone)
        * ransac_voting_gpu.py:2    import path -> plain `import ransac_voting`
        * ransac_voting_gpu.py:36,142  masked_select needs a bool mask on torch>=1.2
-       * torch.solve (removed in torch 2.x) -> torch.linalg.solve shim, otherwise
-         b_inv's bare `except` silently returns the identity (ransac_voting_gpu.py:105-108)
+       * torch.solve (a stub that only raises in torch 2.x) -> torch.linalg.solve shim, otherwise
+         b_inv's bare `except` silently returns the identity (ransac_voting_gpu.py:105-108) and the
+         reference returns ATb -- garbage of magnitude 1e4 px -- without any error
   3. compiles src/ransac_voting_kernel.cu UNMODIFIED with torch's
      BuildExtension for sm_100 (the reference setup.py passes no arch flags;
      TORCH_CUDA_ARCH_LIST=10.0 is what a user on a B200 would get).
@@ -51,7 +52,13 @@ def _patch_py(text):
     text = text.replace(
         "import lib.csrc.ransac_voting.ransac_voting as ransac_voting",
         "import ransac_voting  # [oracle/build_ref.py] import path alias\n"
-        "if not hasattr(torch, 'solve'):  # [oracle/build_ref.py] torch.solve was removed in torch 2.x\n"
+        "def _pvb_solve_works():  # [oracle/build_ref.py] torch.solve exists in torch 2.x but only raises\n"
+        "    try:\n"
+        "        torch.solve(torch.eye(2), torch.eye(2))\n"
+        "        return True\n"
+        "    except Exception:\n"
+        "        return False\n"
+        "if not _pvb_solve_works():\n"
         "    torch.solve = lambda B, A: (torch.linalg.solve(A, B), None)")
     # masked_select requires a bool mask on modern torch
     text = text.replace(

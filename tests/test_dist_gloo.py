@@ -1,0 +1,78 @@
+"""world_size-2 gloo test (CPU) of the N>1 path's host logic: shard bounds, the ragged all_gather and
+global-image-index seeding.  The compute op is injected: on CPU the oracle stands in for the CUDA
+operator (tests may use the oracle as the checker; the product never does)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_op(mask, vertex, hn, inlier_thresh=0.999, min_num=5, max_num=30000, seed=0, img_base=0):
+    import pvnet_oracle
+    out = pvnet_oracle.ransac_voting_layer_v3(mask.numpy(), vertex.numpy(), hn, inlier_thresh=inlier_thresh,
+                                              min_num=min_num, max_num=max_num, seed=seed, img_base=img_base)
+    return torch.from_numpy(out)
+
+
+def _worker(rank, world, port, total, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clean_pvnet_b200 import parallel, synth
+        mask, vertex, _ = synth.make_inputs("tiny", device="cpu", seed=77, B=total)
+        lo, hi = parallel.shard_bounds(total, world, rank)
+        out = parallel.sharded_ransac_voting_layer_v3(mask[lo:hi], vertex[lo:hi], 16, total, inlier_thresh=0.99,
+                                                      max_num=300, seed=5, op=_oracle_op)
+        if rank == 0:
+            q.put(out.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    from clean_pvnet_b200.parallel import shard_bounds
+    for total in (0, 1, 5, 16, 128, 131):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(total, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == total
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gather_equals_single_process():
+    total = 5       # ragged: ranks get 3 and 2 images
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from clean_pvnet_b200 import synth
+    mask, vertex, _ = synth.make_inputs("tiny", device="cpu", seed=77, B=total)
+    want = _oracle_op(mask, vertex, 16, inlier_thresh=0.99, max_num=300, seed=5).numpy()
+    assert got.shape == (total, vertex.shape[3], 2)
+    assert np.array_equal(got, want)

@@ -124,20 +124,38 @@ def _algorithmic_bytes(B, H, W, K, tn_sum, mask_elt=8):
     return B * H * W * mask_elt + tn_sum * K * 8 + B * K * 8
 
 
+def _usable_cores():
+    """Host threads this process can really run: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def _cpu_baseline(mask, vertex, K, seconds_target=15.0):
     """Oracle port (oracle/pvnet_oracle.c) on the host cores: one image per thread at a time."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import pvnet_oracle
     pvnet_oracle.build()
-    cores = os.cpu_count() or 1
+    cores = _usable_cores()
     m = mask.cpu().numpy().astype(np.int64)
     v = vertex.cpu().numpy()
     B = m.shape[0]
     t0 = time.perf_counter()
     pvnet_oracle.ransac_voting_layer_v3(m[:1], v[:1], HN, inlier_thresh=THRESH, seed=1)
     t_one = time.perf_counter() - t0
-    n_img = int(max(1, min(cores * max(1, int(seconds_target / max(t_one, 1e-3))), 4 * cores)))
+    # bounded sample: about `seconds_target` seconds of wall time assuming perfect scaling, at most
+    # two images per thread (host cores share memory bandwidth and, on SMT, FMA pipes)
+    n_img = int(max(1, min(cores * max(1, int(seconds_target / max(t_one, 1e-3))), 2 * cores)))
     done = [0]
     lock = threading.Lock()
 

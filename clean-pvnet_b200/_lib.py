@@ -31,8 +31,10 @@ class PvbDesc(ctypes.Structure):
 
 class PvbLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in
-                ("total", "status", "fgsum", "nz", "tn", "state", "bits", "wordoff", "xy", "dirs", "hyp",
-                 "counts", "win")] + [("nwords", ctypes.c_int32), ("capacity", ctypes.c_int32)]
+                ("total", "status", "fgsum", "nz", "tn", "state", "bits", "wordoff", "blocktot", "xy", "dirs", "hyp",
+                 "counts", "win", "refit_partial", "refit_ticket")] + [
+                    ("nwords", ctypes.c_int32), ("nblocks", ctypes.c_int32), ("capacity", ctypes.c_int32),
+                    ("refit_splits", ctypes.c_int32)]
 
 
 # every symbol include/pvnet_vote_b200.h declares: name -> (restype, argtypes)
@@ -50,6 +52,7 @@ SIGNATURES = {
     "pvb_ransac_voting_v3_host": (ctypes.c_int, [_dp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "pvb_profile_enable": (ctypes.c_int, [_i32]),
     "pvb_profile_reset": (ctypes.c_int, []),
+    "pvb_set_tuning": (ctypes.c_int, [_i32, _i32]),
     "pvb_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), _i32]),
     "pvb_generate_hypothesis": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pvb_voting_for_hypothesis": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _vp]),

@@ -90,24 +90,32 @@ int make_layout(const pvb_desc *d, pvb_layout *L)
     if (rc) return rc;
     const size_t B = (size_t)d->B, K = (size_t)d->K, hn = (size_t)d->hn;
     const int nwords = (int)(((long long)d->H * d->W + 31) / 32);
+    const int nblocks = (nwords + 255) / 256;
     const int cap = default_capacity(d);
+    const int splits = refit_splits_for(cap);
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes); return o; };
+    // header: zeroed at the start of every call (everything before `bits`)
     L->status = take(4 * sizeof(int));
     L->fgsum = take(B * sizeof(unsigned long long));
     L->nz = take(B * sizeof(int));
     L->tn = take(B * sizeof(int));
     L->state = take(B * sizeof(int));
+    L->refit_ticket = take(B * K * sizeof(int));
     L->bits = take(B * nwords * sizeof(uint32_t));
     L->wordoff = take(B * nwords * sizeof(int));
+    L->blocktot = take(B * nblocks * sizeof(int));
     L->xy = take(B * cap * sizeof(float2));
     L->dirs = take(B * K * cap * sizeof(float2));
     L->hyp = take(B * K * hn * sizeof(float2));
     L->counts = take(B * K * hn * sizeof(int));
     L->win = take(B * K * sizeof(float2));
+    L->refit_partial = take(B * K * splits * 5 * sizeof(double));
     L->total = off;
     L->nwords = nwords;
+    L->nblocks = nblocks;
     L->capacity = cap;
+    L->refit_splits = splits;
     return PVB_OK;
 }
 
@@ -116,6 +124,7 @@ struct Plan {
     SelectArgs s;
     VoteArgs v;
     float2 *win;
+    RefitScratch refit;
 };
 
 int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
@@ -134,11 +143,12 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     s.vertex = vertex;
     for (int i = 0; i < 5; ++i) s.vs[i] = d->vertex_stride[i];
     s.selection = selection;
-    s.B = d->B; s.H = d->H; s.W = d->W; s.K = d->K; s.nwords = L.nwords; s.cap = L.capacity;
+    s.B = d->B; s.H = d->H; s.W = d->W; s.K = d->K; s.nwords = L.nwords; s.nblocks = L.nblocks; s.cap = L.capacity;
     s.min_num = d->min_num; s.max_num = d->max_num; s.img_base = d->img_base;
     s.seed = d->seed; s.tag_sel = d->rng_tag_sel ? (uint32_t)d->rng_tag_sel : tag_sel;
     s.bits = reinterpret_cast<uint32_t *>(w + L.bits);
     s.wordoff = reinterpret_cast<int *>(w + L.wordoff);
+    s.blocktot = reinterpret_cast<int *>(w + L.blocktot);
     s.fgsum = reinterpret_cast<unsigned long long *>(w + L.fgsum);
     s.nz = reinterpret_cast<int *>(w + L.nz);
     s.tn = reinterpret_cast<int *>(w + L.tn);
@@ -156,13 +166,16 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     v.hyp = reinterpret_cast<float2 *>(w + L.hyp);
     v.counts = reinterpret_cast<int *>(w + L.counts);
     P->win = reinterpret_cast<float2 *>(w + L.win);
+    P->refit.partial = reinterpret_cast<double *>(w + L.refit_partial);
+    P->refit.ticket = reinterpret_cast<int *>(w + L.refit_ticket);
+    P->refit.splits = L.refit_splits;
     return PVB_OK;
 }
 
 int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
 {
-    // status, fgsum, nz are contiguous at the start of the workspace
-    cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.tn, st);
+    // status, fgsum, nz, tn, state, refit tickets: contiguous at the start of the workspace
+    cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.bits, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(header)");
     e = launch_select(P.s, st);
     if (e != cudaSuccess) return cuda_fail(e, "select kernels");
@@ -209,7 +222,7 @@ PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const floa
     ProfCall *pc = prof_begin(st);
     rc = run_front(P, st, pc);
     if (rc) return rc;
-    cudaError_t e = launch_refit(P.v, P.win, out_kpt, st);
+    cudaError_t e = launch_refit(P.v, P.win, P.refit, out_kpt, st);
     if (e != cudaSuccess) return cuda_fail(e, "refit kernel");
     prof_mark(pc, PVB_STAGE_FINISH, st);
     return PVB_OK;
@@ -365,6 +378,13 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
 }
 
 PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK; }
+
+PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant)
+{
+    if (vote_variant < 0 || vote_variant > 5) return fail(PVB_ERR_INVALID, "vote_variant must be 0..5");
+    set_vote_tuning(vote_chunk, vote_variant);
+    return PVB_OK;
+}
 
 PVB_API int pvb_profile_reset(void)
 {

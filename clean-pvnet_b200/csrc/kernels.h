@@ -13,11 +13,11 @@ struct SelectArgs {
     const float *vertex;
     long long vs[5];              // vertex strides (elements)
     const float *selection;       // optional [B,H,W]
-    int B, H, W, K, nwords, cap, min_num, max_num, img_base;
+    int B, H, W, K, nwords, nblocks, cap, min_num, max_num, img_base;
     uint64_t seed;
     uint32_t tag_sel;
     uint32_t *bits;
-    int *wordoff;
+    int *wordoff, *blocktot;
     unsigned long long *fgsum;
     int *nz, *tn, *state, *status;
     float2 *xy, *dirs;
@@ -44,8 +44,13 @@ struct VoteArgs {
 cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st);
 // counts[b][k][h] = #pixels voting for hyp[b][k][h]   (zeroes counts itself)
 cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st);
-// argmax + winner refit -> out_kpt [B][K][2], win [B][K]
-cudaError_t launch_refit(const VoteArgs &a, float2 *win, float *out_kpt, cudaStream_t st);
+void set_vote_tuning(int chunk, int variant);   // tooling: pixels per CTA, hypotheses-per-thread variant
+// argmax + winner refit -> out_kpt [B][K][2], win [B][K].  The pixels of one (image,keypoint) are split
+// over `splits` CTAs; partial normal equations meet in `partial`, the last CTA to arrive (ticket) adds
+// them in a fixed order and solves, so the result is deterministic.
+struct RefitScratch { double *partial; int *ticket; int splits; };
+int refit_splits_for(int cap);
+cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, cudaStream_t st);
 // ratio/threshold/weighted covariance -> out_cov [B][K][2][2]
 cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, cudaStream_t st);
 

@@ -6,7 +6,8 @@
 //
 // HBM layout produced (see pvb_layout in include/pvnet_vote_b200.h):
 //   bits    uint32[B][nwords]      1 bit per pixel, row-major
-//   wordoff int32 [B][nwords]      exclusive popcount prefix  -> order-preserving compaction
+//   wordoff int32 [B][nwords]      exclusive popcount prefix inside each 256-word block
+//   blocktot int32[B][nblocks]     selected pixels per 256-word block  -> order-preserving compaction
 //   xy      float2[B][cap]         (x,y) of the t-th selected pixel (torch.nonzero order, :140-141)
 //   dirs    float2[B][K][cap]      vertex vectors of the selected pixels, keypoint-major so that a
 //                                  (image,keypoint) vote CTA streams one contiguous float2 array
@@ -27,9 +28,11 @@ template <>
 __device__ __forceinline__ uint32_t mask_byte<double>(double v) { return (uint32_t)(uint8_t)(long long)v; }
 
 constexpr int MB_WARPS = 8;
+constexpr int MB_UNROLL = 8;
 
 // One warp converts 1024 pixels into 32 bitmap words with coalesced loads (lane = pixel within
-// word) and ballots; lane i keeps word i so the 32 words leave as one coalesced store.
+// word) and ballots; lane i keeps word i so the 32 words leave as one coalesced store.  Loads are
+// issued MB_UNROLL at a time before any ballot so that each warp keeps 2 KB (int64 masks) in flight.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(MB_WARPS * 32)
 mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long long sx, int H, int W,
@@ -44,21 +47,28 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
     const T *mb = mask + (long long)b * sb;
     const bool contig = (sx == 1 && sy == W);
     uint32_t myword = 0, sum = 0;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-        const int p = (w0 + i) * 32 + lane;
-        uint32_t val = 0;
-        bool sel = false;
-        if (p < HW) {
-            long long off = p;
-            if (!contig) { const int y = p / W; off = (long long)y * sy + (long long)(p - y * W) * sx; }
-            const T v = __ldg(mb + off);
-            if (MODE == PVB_SELECT_BYTE) { val = mask_byte<T>(v); sel = val != 0; }
-            else { sel = (v == (T)1); val = sel; }
+    for (int i0 = 0; i0 < 32; i0 += MB_UNROLL) {
+        T v[MB_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MB_UNROLL; ++u) {
+            const int p = (w0 + i0 + u) * 32 + lane;
+            v[u] = (T)0;
+            if (p < HW) {
+                long long off = p;
+                if (!contig) { const int y = p / W; off = (long long)y * sy + (long long)(p - y * W) * sx; }
+                v[u] = __ldg(mb + off);
+            }
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, sel);
-        if (lane == i) myword = word;
-        sum += val;
+#pragma unroll
+        for (int u = 0; u < MB_UNROLL; ++u) {
+            uint32_t val;
+            bool sel;
+            if (MODE == PVB_SELECT_BYTE) { val = mask_byte<T>(v[u]); sel = val != 0; }
+            else { sel = (v[u] == (T)1); val = sel; }
+            const uint32_t word = __ballot_sync(0xffffffffu, sel);
+            if (lane == i0 + u) myword = word;
+            sum += val;
+        }
     }
     if (w0 + lane < nwords) bits[(size_t)b * nwords + w0 + lane] = myword;
     const int s = warp_sum((int)sum);
@@ -69,127 +79,142 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
     }
 }
 
-// One CTA per image: decides skip / thinning (ransac_voting_gpu.py:129-138), applies the
-// Bernoulli thinning to the bitmap and writes the exclusive popcount prefix.
-constexpr int SS_THREADS = 1024;
+// One CTA per 256 bitmap words: decides skip / thinning for its image (ransac_voting_gpu.py:129-138),
+// applies the Bernoulli thinning to its words, and writes the exclusive popcount prefix WITHIN the
+// block plus the block total; the gather kernel adds the totals of the preceding blocks.
+constexpr int TS_THREADS = 256;
 
-__global__ void __launch_bounds__(SS_THREADS)
-select_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff,
-                   const unsigned long long *__restrict__ fgsum, int *__restrict__ tn,
-                   int *__restrict__ state, int *__restrict__ status,
-                   const float *__restrict__ selection, int nwords, int HW, int min_num, int max_num,
-                   int cap, uint2 key, uint32_t tag, int img_base)
+__global__ void __launch_bounds__(TS_THREADS)
+thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__restrict__ blocktot,
+                 const unsigned long long *__restrict__ fgsum, int *__restrict__ tn, int *__restrict__ state,
+                 const float *__restrict__ selection, int nwords, int nblocks, int HW, int min_num, int max_num,
+                 uint2 key, uint32_t tag, int img_base)
 {
-    const int b = blockIdx.x;
+    const int b = blockIdx.y, blk = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long fg = fgsum[b];
-    if (fg < (unsigned long long)(min_num < 0 ? 0 : min_num)) {   // :129  (uniform per CTA)
-        if (tid == 0) { state[b] = 1; tn[b] = 0; }
+    if (fg < (unsigned long long)(min_num < 0 ? 0 : min_num)) {   // :129  (uniform per image)
+        if (tid == 0) { if (blk == 0) state[b] = 1; blocktot[(size_t)b * nblocks + blk] = 0; }
         return;
     }
     const bool thin = fg > (unsigned long long)(max_num < 0 ? 0 : max_num);   // :135
     const float ratio = thin ? __fdiv_rn((float)max_num, (float)fg) : 0.f;     // max_num / fg.float()
-    __shared__ int warp_tot[32];
-    uint32_t *bb = bits + (size_t)b * nwords;
-    int *wo = wordoff + (size_t)b * nwords;
-    int base = 0;
-    for (int w0 = 0; w0 < nwords; w0 += SS_THREADS) {
-        const int w = w0 + tid;
-        uint32_t word = (w < nwords) ? bb[w] : 0u;
-        if (thin && word) {
-            uint32_t keep = 0;
-            if (selection) {
-                const float *sp = selection + (size_t)b * HW + (size_t)w * 32;
-                uint32_t m = word;
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (__ldg(sp + j) < ratio) keep |= 1u << j;
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint32_t nib = (word >> (4 * g)) & 0xfu;
-                    if (!nib) continue;
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)w * 8u + g, 0u, (uint32_t)(img_base + b), tag), key);
-                    uint32_t kb = 0;
-                    kb |= (u32_to_unit(r.x) < ratio) ? 1u : 0u;
-                    kb |= (u32_to_unit(r.y) < ratio) ? 2u : 0u;
-                    kb |= (u32_to_unit(r.z) < ratio) ? 4u : 0u;
-                    kb |= (u32_to_unit(r.w) < ratio) ? 8u : 0u;
-                    keep |= (kb & nib) << (4 * g);
-                }
+    const int w = blk * TS_THREADS + tid;
+    uint32_t word = (w < nwords) ? bits[(size_t)b * nwords + w] : 0u;
+    if (thin && word) {
+        uint32_t keep = 0;
+        if (selection) {
+            const float *sp = selection + (size_t)b * HW + (size_t)w * 32;
+            uint32_t m = word;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                if (__ldg(sp + j) < ratio) keep |= 1u << j;
             }
-            word = keep;
-            bb[w] = word;
-        }
-        const int c = __popc(word);
-        int incl = c;
+        } else {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int t = warp_tot[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += v;
+            for (int g = 0; g < 8; ++g) {
+                const uint32_t nib = (word >> (4 * g)) & 0xfu;
+                if (!nib) continue;
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)w * 8u + g, 0u, (uint32_t)(img_base + b), tag), key);
+                uint32_t kb = 0;
+                kb |= (u32_to_unit(r.x) < ratio) ? 1u : 0u;
+                kb |= (u32_to_unit(r.y) < ratio) ? 2u : 0u;
+                kb |= (u32_to_unit(r.z) < ratio) ? 4u : 0u;
+                kb |= (u32_to_unit(r.w) < ratio) ? 8u : 0u;
+                keep |= (kb & nib) << (4 * g);
             }
-            warp_tot[lane] = t;   // inclusive prefix of warp totals
         }
-        __syncthreads();
-        const int warp_excl = warp ? warp_tot[warp - 1] : 0;
-        const int total = warp_tot[31];
-        if (w < nwords) wo[w] = base + warp_excl + incl - c;
-        base += total;
-        __syncthreads();
+        word = keep;
+        bits[(size_t)b * nwords + w] = word;
     }
+    const int c = __popc(word);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    __shared__ int warp_tot[TS_THREADS / 32];
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int warp_excl = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < TS_THREADS / 32; ++i) {
+        const int t = warp_tot[i];
+        if (i < warp) warp_excl += t;
+        total += t;
+    }
+    if (w < nwords) wordoff[(size_t)b * nwords + w] = warp_excl + incl - c;
     if (tid == 0) {
-        state[b] = 0;
-        if (base > cap) {
-            atomicCAS(status, 0, PVB_ERR_CAPACITY);
-            status[1] = b;
-            base = cap;
-        }
-        tn[b] = base;
+        blocktot[(size_t)b * nblocks + blk] = total;
+        if (total) atomicAdd(tn + b, total);
     }
 }
 
-// One warp per bitmap word: lane j owns pixel 32*w+j.  Writes xy[] and gathers the K vertex
-// vectors of each selected pixel into the keypoint-major dirs[] array.
-constexpr int GA_WARPS = 8;
+// One CTA per 256-word block (the thin_scan granularity).  The block's selected pixels are first
+// listed in shared memory (position = the in-block prefix thin_scan left in wordoff[]), then the CTA
+// walks that dense list: every lane is active, loads touch only selected pixels, and each store
+// instruction of a warp writes 32 consecutive t of one keypoint plane of dirs[] (256 B).
+constexpr int GA_THREADS = TS_THREADS;
 
-__global__ void __launch_bounds__(GA_WARPS * 32)
+__global__ void __launch_bounds__(GA_THREADS)
 gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff,
-              const int *__restrict__ state, const float *__restrict__ vertex,
+              const int *__restrict__ blocktot, const int *__restrict__ state, int *__restrict__ tn,
+              int *__restrict__ status, const float *__restrict__ vertex,
               long long sB, long long sH, long long sW, long long sK, long long sC,
-              float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int K, int cap, int W)
+              float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W)
 {
-    const int b = blockIdx.y;
+    __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (13 bits)
+    __shared__ int s_base;
+    const int b = blockIdx.y, blk = blockIdx.x;
     if (state[b] != 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * GA_WARPS + warp;
-    if (w >= nwords) return;
-    const uint32_t word = bits[(size_t)b * nwords + w];
-    if (!((word >> lane) & 1u)) return;
-    const int t = wordoff[(size_t)b * nwords + w] + __popc(word & ((1u << lane) - 1u));
-    if (t >= cap) return;
-    const int p = w * 32 + lane;
-    const int y = p / W, x = p - y * W;
-    xy[(size_t)b * cap + t] = make_float2((float)x, (float)y);
-    const float *vb = vertex + (long long)b * sB + (long long)y * sH + (long long)x * sW;
-    float2 *db = dirs + (size_t)b * K * cap + t;
-    if (sC == 1 && (sK & 1) == 0 && ((reinterpret_cast<uintptr_t>(vb) & 7u) == 0)) {
-        for (int k = 0; k < K; ++k)
-            db[(size_t)k * cap] = __ldg(reinterpret_cast<const float2 *>(vb + (long long)k * sK));
-    } else {
-        for (int k = 0; k < K; ++k) {
-            const float *q = vb + (long long)k * sK;
-            db[(size_t)k * cap] = make_float2(__ldg(q), __ldg(q + sC));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (blk == 0 && tid == 0 && tn[b] > cap) {
+        // more pixels selected than the workspace holds: report, clamp (nobody in this kernel reads tn)
+        atomicCAS(status, 0, PVB_ERR_CAPACITY);
+        status[1] = b;
+        tn[b] = cap;
+    }
+    const int total = blocktot[(size_t)b * nblocks + blk];
+    if (total == 0) return;
+    if (warp == 0) {   // offset of this block = totals of the preceding blocks
+        int base = 0;
+        for (int i = lane; i < blk; i += 32) base += blocktot[(size_t)b * nblocks + i];
+        base = warp_sum(base);
+        if (lane == 0) s_base = base;
+    }
+    const int w = blk * TS_THREADS + tid;
+    if (w < nwords) {
+        uint32_t word = bits[(size_t)b * nwords + w];
+        int o = wordoff[(size_t)b * nwords + w];
+        while (word) {
+            const int j = __ffs(word) - 1;
+            word &= word - 1;
+            s_list[o++] = (unsigned short)(tid * 32 + j);
+        }
+    }
+    __syncthreads();
+    const int base = s_base;
+    const bool vec = (sC == 1 && (sK & 1) == 0 && (sW & 1) == 0 && (sH & 1) == 0 && (sB & 1) == 0 &&
+                      (reinterpret_cast<uintptr_t>(vertex) & 7u) == 0);
+    const float *vimg = vertex + (long long)b * sB;
+    for (int i = tid; i < total; i += GA_THREADS) {
+        const int t = base + i;
+        if (t >= cap) break;
+        const int p = blk * (TS_THREADS * 32) + (int)s_list[i];
+        const int y = p / W, x = p - y * W;
+        xy[(size_t)b * cap + t] = make_float2((float)x, (float)y);
+        const float *vb = vimg + (long long)y * sH + (long long)x * sW;
+        float2 *db = dirs + (size_t)b * K * cap + t;
+        if (vec) {
+            for (int k = 0; k < K; ++k)
+                db[(size_t)k * cap] = __ldg(reinterpret_cast<const float2 *>(vb + (long long)k * sK));
+        } else {
+            for (int k = 0; k < K; ++k) {
+                const float *q = vb + (long long)k * sK;
+                db[(size_t)k * cap] = make_float2(__ldg(q), __ldg(q + sC));
+            }
         }
     }
 }
@@ -221,15 +246,17 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
 #undef PVB_MB
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    select_scan_kernel<<<a.B, SS_THREADS, 0, st>>>(a.bits, a.wordoff, a.fgsum, a.tn, a.state, a.status,
-                                                   a.selection, nwords, a.H * a.W, a.min_num, a.max_num,
-                                                   a.cap, make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)),
-                                                   a.tag_sel, a.img_base);
+    dim3 g2(a.nblocks, a.B);
+    thin_scan_kernel<<<g2, TS_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.fgsum, a.tn, a.state, a.selection,
+                                                nwords, a.nblocks, a.H * a.W, a.min_num, a.max_num,
+                                                make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.tag_sel,
+                                                a.img_base);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 g3((nwords + GA_WARPS - 1) / GA_WARPS, a.B);
-    gather_kernel<<<g3, GA_WARPS * 32, 0, st>>>(a.bits, a.wordoff, a.state, a.vertex, a.vs[0], a.vs[1], a.vs[2],
-                                                a.vs[3], a.vs[4], a.xy, a.dirs, nwords, a.K, a.cap, a.W);
+    dim3 g3(a.nblocks, a.B);
+    gather_kernel<<<g3, GA_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
+                                                a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
+                                                a.nblocks, a.K, a.cap, a.W);
     return cudaGetLastError();
 }
 

@@ -32,7 +32,7 @@ generate_kernel(VoteArgs a)
     const int h = blockIdx.x * 256 + threadIdx.x;
     if (h >= a.hn) return;
     const int k = blockIdx.y, b = blockIdx.z;
-    const int tn = a.tn[b];
+    const int tn = min(a.tn[b], a.cap);
     float x = 0.f, y = 0.f;
     if (tn > 0) {
         int t0, t1;
@@ -72,118 +72,195 @@ struct VoteK {
     int chunk;     // pixels per CTA (multiple of VOTE_TILE)
 };
 
-constexpr int VOTE_TILE = 256;
+constexpr int VOTE_TILE = 256;    // pixels per CTA, staged in shared memory
+constexpr int VOTE_BLOCK = 16;    // pixels per unrolled block (one guard-band check per block)
 
-template <int HPT, int NT>
-__global__ void __launch_bounds__(NT)
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// Cone margin of one pixel record against one hypothesis: m = kappa*u.(h-c) - |u_perp.(h-c)|.
+// The same function is used by the fast path and by the guard-band re-check, so both see the
+// same value bit for bit.
+__device__ __forceinline__ float cone_margin(const float4 ra, const float2 rb, float hxc, float hyc)
+{
+    const float ap = fmaf(ra.x, hxc, fmaf(ra.y, hyc, ra.z));
+    const float pp = fmaf(ra.w, hxc, fmaf(rb.x, hyc, rb.y));
+    return ap - fabsf(pp);
+}
+
+template <int HPT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 vote_kernel(const VoteK p)
 {
-    __shared__ float4 s_a[VOTE_TILE];   // (A1, A2, A3, B1)
-    __shared__ float2 s_b[VOTE_TILE];   // (B2, B3)
+    constexpr int PPT = VOTE_TILE / NT;               // pixels staged per thread
+    constexpr int NW = NT / 32;
+    __shared__ __align__(16) float4 s_a[VOTE_TILE];   // (A1, A2, A3, B1)
+    __shared__ __align__(16) float2 s_b[VOTE_TILE];   // (B2, B3)
+    __shared__ float s_box[4][NW];
     const VoteArgs &a = p.a;
     const int b = blockIdx.z;
     const int k = blockIdx.y % a.K, slice = blockIdx.y / a.K;
-    const int tn = a.tn[b];
-    const int start = blockIdx.x * p.chunk;
-    if (start >= tn) return;
-    const int end = min(start + p.chunk, tn);
-    const int tid = threadIdx.x;
-
-    const float ox = p.cone.ox, oy = p.cone.oy, kappa = p.cone.kappa, thresh = p.cone.thresh;
-    const float cmax = a.cmax_dev ? __ldg(a.cmax_dev) : p.cone.cmax;
+    const int tn = min(a.tn[b], a.cap);
+    const int t0 = blockIdx.x * VOTE_TILE;
+    if (t0 >= tn) return;
+    const int n = min(VOTE_TILE, tn - t0);
+    const int npad = (n + VOTE_BLOCK - 1) / VOTE_BLOCK * VOTE_BLOCK;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float kappa = p.cone.kappa, thresh = p.cone.thresh;
     const float2 *hyp = a.hyp + ((size_t)b * a.K + k) * a.hn;
+    const float2 *xy = a.xy + (size_t)b * a.cap + t0;
+    const float2 *dk = a.dirs + ((size_t)b * a.K + k) * a.cap + t0;
+    const int hbase = slice * (NT * HPT) + tid;
 
-    float hx[HPT], hy[HPT], hxc[HPT], hyc[HPT];
-    int cnt[HPT];
-    float dmax = 1e-30f;
+    // ---- stage 1: load this tile's pixels, bounding box -> tile-local origin for the fast path.
+    // The guard band scales with S = |h-o|_1 + max|c-o|_1, so a local origin keeps it tight.
+    float2 v[PPT], c[PPT];
+    float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
 #pragma unroll
-    for (int j = 0; j < HPT; ++j) {
-        const int h = slice * (NT * HPT) + j * NT + tid;
-        const float2 q = (h < a.hn) ? hyp[h] : make_float2(0.f, 0.f);
-        hx[j] = q.x; hy[j] = q.y;
-        float xc = q.x - ox, yc = q.y - oy;
-        const float S = fabsf(xc) + fabsf(yc) + cmax;
-        float d = p.cone.band * S;
-        if (!(S <= 1e15f) || !(d < CUDART_INF_F)) { xc = 0.f; yc = 0.f; d = CUDART_INF_F; }   // exact path only
-        hxc[j] = xc; hyc[j] = yc;
-        dmax = fmaxf(dmax, d);
-        cnt[j] = 0;
+    for (int r = 0; r < PPT; ++r) {
+        const int i = tid + r * NT;
+        v[r] = make_float2(0.f, 0.f); c[r] = make_float2(0.f, 0.f);
+        if (i < n) {
+            v[r] = __ldg(dk + i); c[r] = __ldg(xy + i);
+            x0 = fminf(x0, c[r].x); x1 = fmaxf(x1, c[r].x); y0 = fminf(y0, c[r].y); y1 = fmaxf(y1, c[r].y);
+        }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (lane == 0) { s_box[0][warp] = x0; s_box[1][warp] = x1; s_box[2][warp] = y0; s_box[3][warp] = y1; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        x0 = fminf(x0, s_box[0][w]); x1 = fmaxf(x1, s_box[1][w]); y0 = fminf(y0, s_box[2][w]); y1 = fmaxf(y1, s_box[3][w]);
+    }
+    const float ox = 0.5f * (x0 + x1), oy = 0.5f * (y0 + y1);
+    // max over the tile of |cx-ox|+|cy-oy| (half extents, padded against the rounding of ox/oy)
+    const float cmax = (0.5f * (x1 - x0) + 0.5f * (y1 - y0)) * 1.000001f + 1e-3f;
 
-    const float2 *xy = a.xy + (size_t)b * a.cap;
-    const float2 *dk = a.dirs + ((size_t)b * a.K + k) * a.cap;
-
-    for (int t0 = start; t0 < end; t0 += VOTE_TILE) {
-        const int n = min(VOTE_TILE, end - t0);
-        __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            const float2 v = __ldg(dk + t0 + i);
-            const float2 c = __ldg(xy + t0 + i);
-            const float n1 = __fsqrt_rn(__fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)));   // the reference's norm1
-            float4 ra; float2 rb;
-            const float cxc = c.x - ox, cyc = c.y - oy;
-            if (!(n1 > __int_as_float(0x358637BD))) {
-                // (double)norm1 < 1e-6 or NaN: the reference never votes for this pixel (.cu:121)
-                ra = make_float4(0.f, 0.f, -1e30f, 0.f); rb = make_float2(0.f, 0.f);
-            } else if (!(n1 < 1e18f) || !(fabsf(cxc) + fabsf(cyc) <= cmax)) {
-                // outside the domain of the error analysis: force the exact path (m == 0 < dmax)
-                ra = make_float4(0.f, 0.f, 0.f, 0.f); rb = make_float2(0.f, 0.f);
-            } else {
-                const float inv = 1.0f / n1;
-                const float ux = v.x * inv, uy = v.y * inv;
-                const float a1 = kappa * ux, a2 = kappa * uy;
-                ra.x = a1; ra.y = a2; ra.z = -fmaf(a1, cxc, a2 * cyc);
-                ra.w = -uy; rb.x = ux; rb.y = fmaf(uy, cxc, -(ux * cyc));
+    // ---- stage 2: cone records
+#pragma unroll
+    for (int r = 0; r < PPT; ++r) {
+        const int i = tid + r * NT;
+        if (i < npad) {
+            // pad record == "never votes": margin -1e30, negative, never inside a finite band
+            float4 ra = make_float4(0.f, 0.f, -1e30f, 0.f);
+            float2 rb = make_float2(0.f, 0.f);
+            if (i < n) {
+                const float n1 = __fsqrt_rn(__fmaf_rn(v[r].x, v[r].x, __fmul_rn(v[r].y, v[r].y)));   // the reference's norm1
+                const float cxc = c[r].x - ox, cyc = c[r].y - oy;
+                if (!(n1 > __int_as_float(0x358637BD))) {
+                    // (double)norm1 < 1e-6 or NaN: the reference never votes for this pixel (.cu:121)
+                } else if (!(n1 < 1e18f) || !(fabsf(cxc) + fabsf(cyc) <= cmax)) {
+                    // outside the domain of the error analysis: force the exact path (m == 0 < delta)
+                    ra.z = 0.f;
+                } else {
+                    const float inv = 1.0f / n1;
+                    const float ux = v[r].x * inv, uy = v[r].y * inv;
+                    const float a1 = kappa * ux, a2 = kappa * uy;
+                    ra.x = a1; ra.y = a2; ra.z = -fmaf(a1, cxc, a2 * cyc);
+                    ra.w = -uy; rb.x = ux; rb.y = fmaf(uy, cxc, -(ux * cyc));
+                }
             }
             s_a[i] = ra; s_b[i] = rb;
         }
-        __syncthreads();
-#pragma unroll 2
-        for (int i = 0; i < n; ++i) {
-            const float4 ra = s_a[i];
-            const float2 rb = s_b[i];
-            bool f[HPT];
-            float mn = CUDART_INF_F;
+    }
+
+    // ---- hypotheses of this thread, relative to the tile origin
+    float hxc[HPT], hyc[HPT], dl[HPT];
+    int neg[HPT];   // tests whose margin is negative (sign bit) = non-inliers, padding included
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {
+        const int h = hbase + j * NT;
+        const float2 q = (h < a.hn) ? hyp[h] : make_float2(0.f, 0.f);
+        float xc = q.x - ox, yc = q.y - oy;
+        const float S = fabsf(xc) + fabsf(yc) + cmax;
+        float d = fmaxf(p.cone.band * S, 1e-30f);
+        if (!(S <= 1e15f) || !(d < CUDART_INF_F)) { xc = 0.f; yc = 0.f; d = CUDART_INF_F; }   // exact path only
+        hxc[j] = xc; hyc[j] = yc; dl[j] = d;
+        neg[j] = 0;
+    }
+    __syncthreads();
+
+    const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(s_a);
+    const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(s_b);
+    for (int i0 = 0; i0 < npad; i0 += VOTE_BLOCK) {
+        const uint32_t sa = sa0 + (uint32_t)i0 * 16u, sb = sb0 + (uint32_t)i0 * 8u;
+        float mn[HPT];   // smallest |margin| of each hypothesis over this block
+#pragma unroll
+        for (int j = 0; j < HPT; ++j) mn[j] = CUDART_INF_F;
+#pragma unroll
+        for (int u = 0; u < VOTE_BLOCK; u += 2) {
+            const float4 ra0 = lds128(sa + u * 16), ra1 = lds128(sa + u * 16 + 16);
+            const float4 rbb = lds128(sb + u * 8);          // (B2,B3) of pixels u and u+1
 #pragma unroll
             for (int j = 0; j < HPT; ++j) {
-                const float ap = fmaf(ra.x, hxc[j], fmaf(ra.y, hyc[j], ra.z));
-                const float pp = fmaf(ra.w, hxc[j], fmaf(rb.x, hyc[j], rb.y));
-                const float m = ap - fabsf(pp);
-                f[j] = m > 0.f;
-                mn = fminf(mn, fabsf(m));
+                const float m0 = cone_margin(ra0, make_float2(rbb.x, rbb.y), hxc[j], hyc[j]);
+                const float m1 = cone_margin(ra1, make_float2(rbb.z, rbb.w), hxc[j], hyc[j]);
+                neg[j] += (int)(__float_as_uint(m0) >> 31);
+                neg[j] += (int)(__float_as_uint(m1) >> 31);
+                mn[j] = fminf(mn[j], fminf(fabsf(m0), fabsf(m1)));
             }
-            if (__builtin_expect(mn < dmax, 0)) {
-                const float2 v = __ldg(dk + t0 + i);
-                const float2 c = __ldg(xy + t0 + i);
+        }
+        bool flag = false;
 #pragma unroll
-                for (int j = 0; j < HPT; ++j) f[j] = vote_exact(v.x, v.y, c.x, c.y, hx[j], hy[j], thresh);
+        for (int j = 0; j < HPT; ++j) flag |= mn[j] < dl[j];
+        if (flag) {
+            // rare: a margin of this block lies inside the guard band -> redo exactly those tests with the
+            // reference's operation sequence and correct the tally (fast verdict = sign bit of m)
+            const int nb = min(VOTE_BLOCK, n - i0);      // padding stays "not an inlier"
+            for (int u = 0; u < nb; ++u) {
+                const int i = i0 + u;
+                const float4 ra = s_a[i];
+                const float2 rb = s_b[i];
+#pragma unroll
+                for (int j = 0; j < HPT; ++j) {
+                    if (mn[j] < dl[j]) {
+                        const float m = cone_margin(ra, rb, hxc[j], hyc[j]);
+                        if (fabsf(m) < dl[j]) {
+                            const int h = hbase + j * NT;
+                            const float2 q = (h < a.hn) ? hyp[h] : make_float2(0.f, 0.f);
+                            const float2 vv = __ldg(dk + i);
+                            const float2 cc = __ldg(xy + i);
+                            const bool in = vote_exact(vv.x, vv.y, cc.x, cc.y, q.x, q.y, thresh);
+                            neg[j] += (in ? 0 : 1) - (int)(__float_as_uint(m) >> 31);
+                        }
+                    }
+                }
             }
-#pragma unroll
-            for (int j = 0; j < HPT; ++j) cnt[j] += f[j] ? 1 : 0;
         }
     }
     int *counts = a.counts + ((size_t)b * a.K + k) * a.hn;
 #pragma unroll
     for (int j = 0; j < HPT; ++j) {
-        const int h = slice * (NT * HPT) + j * NT + tid;
-        if (h < a.hn && cnt[j]) atomicAdd(counts + h, cnt[j]);
+        const int h = hbase + j * NT;
+        const int cnt = npad - neg[j];
+        if (h < a.hn && cnt) atomicAdd(counts + h, cnt);
     }
 }
 
-// Host side of the guard band (DESIGN.md "Guard band"): u = 2^-24,
-//   band = SAFETY * u * (20 + 22*kappa + 10*G),  G = 1/(t*sqrt(1-t^2)).
-ConeParams make_cone(float thresh, int W, int H, float ox, float oy, bool default_origin)
+// Host side of the guard band (DESIGN.md "Guard band"), u = 2^-24:
+//   a test is re-evaluated exactly when |m| < band * S,  S = |hx-ox| + |hy-oy| + max_tile(|cx-ox|+|cy-oy|)
+//   band = 1.25 * u * (18 + 22*kappa + 9*G),  kappa = sqrt(1-t^2)/t,  G = 1/(t*sqrt(1-t^2)).
+// 2*(9+11*kappa)*u*S bounds twice the rounding error of m itself; 9*G*u*|h-c| is how far the reference's
+// fp32 cos can sit from the exact one, mapped into units of m; |h-c| <= S.  tools/band_check.c finds the
+// largest |m| of a fast/exact disagreement at 0.35x this bound (1e8 boundary samples).
+ConeParams make_cone(float thresh)
 {
     ConeParams c;
     c.thresh = thresh;
-    if (default_origin) { ox = 0.5f * (float)(W - 1); oy = 0.5f * (float)(H - 1); }
-    c.ox = ox; c.oy = oy;
-    c.cmax = 0.5f * (float)(W - 1) + 0.5f * (float)(H - 1) + 1.0f;
+    c.ox = c.oy = c.cmax = 0.f;   // the origin is chosen per pixel tile inside the kernel
     const double t = (double)thresh;
     if (t > 0.0 && t < 1.0) {
         const double s = sqrt(1.0 - t * t);
         const double kappa = s / t, G = 1.0 / (t * s);
-        const double band = 2.0 * ldexp(1.0, -24) * (20.0 + 22.0 * kappa + 10.0 * G);
+        const double band = 1.25 * ldexp(1.0, -24) * (18.0 + 22.0 * kappa + 9.0 * G);
         c.kappa = (float)kappa;
         c.band = nextafterf((float)band, INFINITY);
     } else {
@@ -193,24 +270,37 @@ ConeParams make_cone(float thresh, int W, int H, float ox, float oy, bool defaul
     return c;
 }
 
+static int g_vote_variant = 0;      // 0: 4 hyps/thread x 128 threads, 1: 8 hyps/thread x 64 threads
+
+void set_vote_tuning(int chunk, int variant)
+{
+    (void)chunk;   // one 256-pixel tile per CTA (tile-local origin); kept for ABI stability
+    g_vote_variant = variant;
+}
+
 cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(a.counts, 0, sizeof(int) * (size_t)a.B * a.K * a.hn, st);
     if (e != cudaSuccess) return e;
     VoteK p;
     p.a = a;
-    p.cone = make_cone(a.thresh, a.W, a.H, a.ox, a.oy, a.cmax_dev == nullptr);
-    p.chunk = 1024;
-    const int chunks = (a.cap + p.chunk - 1) / p.chunk;
-#define PVB_VOTE(HPT, NT)                                                               \
+    p.cone = make_cone(a.thresh);
+    p.chunk = VOTE_TILE;
+    const int chunks = (a.cap + VOTE_TILE - 1) / VOTE_TILE;
+#define PVB_VOTE(HPT, NT, MINB)                                                         \
     do {                                                                                \
         const int slices = (a.hn + (HPT) * (NT) - 1) / ((HPT) * (NT));                  \
         dim3 g(chunks, a.K * slices, a.B);                                              \
-        vote_kernel<HPT, NT><<<g, NT, 0, st>>>(p);                                      \
+        vote_kernel<HPT, NT, MINB><<<g, NT, 0, st>>>(p);                                \
     } while (0)
-    if (a.hn <= 128) PVB_VOTE(1, 128);
-    else if (a.hn <= 256) PVB_VOTE(2, 128);
-    else PVB_VOTE(4, 128);
+    if (a.hn <= 128) PVB_VOTE(1, 128, 1);
+    else if (a.hn <= 256) PVB_VOTE(2, 128, 1);
+    else if (g_vote_variant == 1) PVB_VOTE(8, 64, 1);
+    else if (g_vote_variant == 2) PVB_VOTE(4, 128, 10);
+    else if (g_vote_variant == 5) PVB_VOTE(4, 128, 1);
+    else if (g_vote_variant == 3) PVB_VOTE(4, 128, 12);
+    else if (g_vote_variant == 4) PVB_VOTE(8, 64, 16);
+    else PVB_VOTE(4, 128, 8);
 #undef PVB_VOTE
     return cudaGetLastError();
 }
@@ -219,19 +309,26 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
 // winner (torch.max semantics: first maximal index, ransac_voting_gpu.py:160-167) + least-squares
 // refit over the winner's inliers (:177-196).  One CTA per (image, keypoint).
 // ---------------------------------------------------------------------------------
-constexpr int RF_THREADS = 256;
+constexpr int RF_THREADS = 128;
+constexpr int RF_CHUNK = 2048;     // pixels per CTA
+
+int refit_splits_for(int cap) { return (cap + RF_CHUNK - 1) / RF_CHUNK; }
 
 __global__ void __launch_bounds__(RF_THREADS)
-refit_kernel(VoteArgs a, float2 *__restrict__ win, float *__restrict__ out)
+refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__restrict__ out)
 {
-    const int k = blockIdx.x, b = blockIdx.y;
+    const int split = blockIdx.x, k = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tn = a.tn[b];
+    constexpr int NW = RF_THREADS / 32;
+    const int tn = min(a.tn[b], a.cap);
     const size_t bk = (size_t)b * a.K + k;
     if (a.state[b] != 0 || tn <= 0) {   // :129-132 -> zeros
-        if (tid == 0) { out[bk * 2] = 0.f; out[bk * 2 + 1] = 0.f; win[bk] = make_float2(0.f, 0.f); }
+        if (split == 0 && tid == 0) { out[bk * 2] = 0.f; out[bk * 2 + 1] = 0.f; win[bk] = make_float2(0.f, 0.f); }
         return;
     }
+    const int nsplit = (tn + RF_CHUNK - 1) / RF_CHUNK;   // CTAs that have pixels for this image
+    if (split >= nsplit) return;
+    // winner: every CTA of this (image,keypoint) finds it on its own (hn counts, L2-resident)
     const int *counts = a.counts + bk * a.hn;
     int bc = -1, bh = 0x7fffffff;
     for (int h = tid; h < a.hn; h += RF_THREADS) {
@@ -243,26 +340,25 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, float *__restrict__ out)
         const int oc = __shfl_xor_sync(0xffffffffu, bc, o), oh = __shfl_xor_sync(0xffffffffu, bh, o);
         if (oc > bc || (oc == bc && oh < bh)) { bc = oc; bh = oh; }
     }
-    __shared__ int s_c[RF_THREADS / 32], s_h[RF_THREADS / 32];
-    __shared__ float2 s_win;
-    __shared__ double s_acc[RF_THREADS / 32][5];
+    __shared__ int s_c[NW], s_h[NW];
+    __shared__ double s_acc[NW][5];
+    __shared__ int s_last;
     if (lane == 0) { s_c[warp] = bc; s_h[warp] = bh; }
     __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < RF_THREADS / 32; ++w)
-            if (s_c[w] > bc || (s_c[w] == bc && s_h[w] < bh)) { bc = s_c[w]; bh = s_h[w]; }
-        // all_win_ratio starts at 0 and is replaced only by a strictly larger ratio (:165-167)
-        s_win = (bc > 0) ? a.hyp[bk * a.hn + bh] : make_float2(0.f, 0.f);
-        win[bk] = s_win;
-    }
-    __syncthreads();
-    const float wx = s_win.x, wy = s_win.y;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        if (s_c[w] > bc || (s_c[w] == bc && s_h[w] < bh)) { bc = s_c[w]; bh = s_h[w]; }
+    // all_win_ratio starts at 0 and is replaced only by a strictly larger ratio (:165-167)
+    const float2 wpt = (bc > 0) ? a.hyp[bk * a.hn + bh] : make_float2(0.f, 0.f);
+    if (split == 0 && tid == 0) win[bk] = wpt;
+
     const float2 *xy = a.xy + (size_t)b * a.cap;
     const float2 *dk = a.dirs + bk * a.cap;
+    const int t_end = min(tn, (split + 1) * RF_CHUNK);
     double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
-    for (int t = tid; t < tn; t += RF_THREADS) {
+    for (int t = split * RF_CHUNK + tid; t < t_end; t += RF_THREADS) {
         const float2 v = __ldg(dk + t), c = __ldg(xy + t);
-        if (vote_exact(v.x, v.y, c.x, c.y, wx, wy, a.thresh)) {
+        if (vote_exact(v.x, v.y, c.x, c.y, wpt.x, wpt.y, a.thresh)) {
             const double nx = (double)v.y, ny = -(double)v.x;       // normal = (d_y, -d_x)  (:178-180)
             const double bb = nx * (double)c.x + ny * (double)c.y;   // b = n . c             (:189)
             a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;          // ATA                   (:190)
@@ -273,21 +369,32 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, float *__restrict__ out)
     if (lane == 0) { s_acc[warp][0] = a00; s_acc[warp][1] = a01; s_acc[warp][2] = a11; s_acc[warp][3] = b0; s_acc[warp][4] = b1; }
     __syncthreads();
     if (tid == 0) {
-        double s[5] = {0, 0, 0, 0, 0};
-        for (int w = 0; w < RF_THREADS / 32; ++w)
-            for (int i = 0; i < 5; ++i) s[i] += s_acc[w][i];
-        const double det = s[0] * s[2] - s[1] * s[1];
-        float x, y;
-        if (det == 0.0 || !isfinite(det)) { x = (float)s[3]; y = (float)s[4]; }   // b_inv's identity fallback (:105-108)
-        else { x = (float)((s[2] * s[3] - s[1] * s[4]) / det); y = (float)((s[0] * s[4] - s[1] * s[3]) / det); }
-        out[bk * 2] = x; out[bk * 2 + 1] = y;
+        double *pp = rs.partial + (bk * rs.splits + split) * 5;
+        for (int i = 0; i < 5; ++i) {
+            double s = 0;
+            for (int w = 0; w < NW; ++w) s += s_acc[w][i];
+            __stcg(pp + i, s);
+        }
+        __threadfence();
+        s_last = (atomicAdd(rs.ticket + bk, 1) == nsplit - 1);
     }
+    __syncthreads();
+    if (!s_last || tid != 0) return;
+    __threadfence();
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int sp = 0; sp < nsplit; ++sp)            // fixed order -> deterministic sums
+        for (int i = 0; i < 5; ++i) s[i] += __ldcg(rs.partial + (bk * rs.splits + sp) * 5 + i);
+    const double det = s[0] * s[2] - s[1] * s[1];
+    float x, y;
+    if (det == 0.0 || !isfinite(det)) { x = (float)s[3]; y = (float)s[4]; }   // b_inv's identity fallback (:105-108)
+    else { x = (float)((s[2] * s[3] - s[1] * s[4]) / det); y = (float)((s[0] * s[4] - s[1] * s[3]) / det); }
+    out[bk * 2] = x; out[bk * 2 + 1] = y;
 }
 
-cudaError_t launch_refit(const VoteArgs &a, float2 *win, float *out_kpt, cudaStream_t st)
+cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, cudaStream_t st)
 {
-    dim3 g(a.K, a.B);
-    refit_kernel<<<g, RF_THREADS, 0, st>>>(a, win, out_kpt);
+    dim3 g(rs.splits, a.K, a.B);
+    refit_kernel<<<g, RF_THREADS, 0, st>>>(a, win, rs, out_kpt);
     return cudaGetLastError();
 }
 
@@ -302,7 +409,7 @@ covariance_kernel(VoteArgs a, const float *__restrict__ mean, float *__restrict_
     const int k = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t bk = (size_t)b * a.K + k;
-    const int tn = a.tn[b];
+    const int tn = min(a.tn[b], a.cap);
     const bool skipped = a.state[b] != 0;          // :211-216  hyp zeros, ratio ones
     const int *counts = a.counts + bk * a.hn;
     const float2 *hyp = a.hyp + bk * a.hn;

@@ -101,14 +101,19 @@ typedef struct pvb_layout {
     size_t tn;       /* int32[B]   selected pixel count after thinning (0 when skipped) */
     size_t state;    /* int32[B]   0 ok, 1 skipped (fg < min_num) */
     size_t bits;     /* uint32[B][nwords] selection bitmap, bit j of word w = pixel 32*w+j */
-    size_t wordoff;  /* int32[B][nwords]  exclusive prefix of popcounts */
+    size_t wordoff;  /* int32[B][nwords]  exclusive prefix of popcounts inside each 256-word block */
+    size_t blocktot; /* int32[B][nblocks] selected pixels per 256-word block */
     size_t xy;       /* float2[B][capacity]   (x,y) of the t-th selected pixel, row-major (torch.nonzero) order */
     size_t dirs;     /* float2[B][K][capacity] gathered vertex vectors (k-major) */
     size_t hyp;      /* float2[B][K][hn] */
     size_t counts;   /* int32[B][K][hn] */
     size_t win;      /* float2[B][K] winning hypothesis before the refit */
+    size_t refit_partial; /* double[B][K][refit_splits][5] partial normal equations */
+    size_t refit_ticket;  /* int32[B][K] arrival counters of the refit CTAs */
     int32_t nwords;  /* ceil(H*W/32) */
+    int32_t nblocks; /* ceil(nwords/256) */
     int32_t capacity;
+    int32_t refit_splits;
 } pvb_layout;
 
 PVB_API int pvb_version(void);
@@ -166,6 +171,10 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_FINISH = 3,   /* winner + refit, or covariance */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
+/* Launch-shape tuning of the vote kernel (tooling; process-wide).  vote_chunk: pixels per CTA (multiple
+ * of 256, <=0 keeps the current value); vote_variant: 0 = 4 hypotheses/thread x 128 threads,
+ * 1 = 8 hypotheses/thread x 64 threads.  Results do not depend on either. */
+PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);
 PVB_API int pvb_profile_read(double *ms, int32_t n);
 

@@ -73,16 +73,48 @@ def test_v3_matches_reference_under_same_seed(pvb, ref, cfg, hn, max_num, seed):
     assert err < 1e-3, err
 
 
+def _exact_refit(ext, dbg, thresh):
+    """The reference's refit formula (ransac_voting_gpu.py:177-196) in float64 on the inlier set the
+    reference extension itself produces for the winning hypotheses -- the value both implementations
+    approximate (the reference in fp32 through cuBLAS matmul + torch.sum + LU)."""
+    B, K = dbg["win"].shape[:2]
+    out = torch.zeros((B, K, 2), dtype=torch.float64, device="cuda")
+    for b in range(B):
+        tn = int(dbg["tn"][b])
+        direct = dbg["dirs"][b, :, :tn].permute(1, 0, 2).contiguous()
+        coords = dbg["xy"][b, :tn].contiguous()
+        inl = torch.zeros((1, K, tn), dtype=torch.uint8, device="cuda")
+        ext.voting_for_hypothesis(direct, coords, dbg["win"][b][None].contiguous(), inl, thresh)
+        w = inl[0].double()                                           # [K,tn]
+        normal = torch.stack([direct[:, :, 1], -direct[:, :, 0]], dim=-1).double().permute(1, 0, 2) * w[:, :, None]
+        bb = (normal * coords.double()[None]).sum(2)                  # [K,tn]
+        ATA = normal.transpose(1, 2) @ normal
+        ATb = (normal * bb[:, :, None]).sum(1)
+        out[b] = torch.linalg.solve(ATA, ATb[:, :, None])[:, :, 0]
+    return out
+
+
 def test_v3_full_size_matches_reference(pvb, ref):
-    """cfg-2 shape, 2 images: thinning (fg ~ 92k > 30000) + 512 hypotheses, strided production layout."""
-    _, gpu = ref
+    """cfg-2 shape, 2 images: thinning (fg ~ 92k > 30000) + 512 hypotheses, strided production layout.
+
+    With ~22 000 inliers per keypoint the reference's fp32 normal equations (cuBLAS matmul + torch.sum,
+    ransac_voting_gpu.py:189-193) carry ~1e-2 px of their own rounding noise on the ill-conditioned
+    out-of-image keypoint, so 1e-3 px agreement is not defined by the reference itself.  The test pins
+    what is: same winners, our refit within 1e-4 px of the exact (float64) value of the reference's
+    formula, and the whole reference-vs-ours gap explained by the reference's distance to that value."""
+    ext, gpu = ref
     mask, vertex, _ = _inputs("cfg2", seed=77, B=2, layout="planar")
     torch.manual_seed(3)
     want = gpu.ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99)
     torch.manual_seed(3)
-    got = pvb.ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99, rng="torch")
-    err = (got - want).norm(dim=-1).max().item()
-    assert err < 1e-3, err
+    got, dbg = pvb.ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99, rng="torch", debug=True)
+    exact = _exact_refit(ext, dbg, 0.99)
+    ours_vs_exact = (got.double() - exact).norm(dim=-1).max().item()
+    ref_vs_exact = (want.double() - exact).norm(dim=-1)
+    ours_vs_ref = (got - want).norm(dim=-1)
+    assert ours_vs_exact < 1e-4, ours_vs_exact
+    assert (ours_vs_ref.double() <= ref_vs_exact + 2e-4).all(), (ours_vs_ref, ref_vs_exact)
+    assert ours_vs_ref.max().item() < 5e-2          # same consensus set; fp32 noise only (measured: 3e-4 .. 1.1e-2 px)
 
 
 def test_distribution_matches_reference_under_same_seed(pvb, ref):

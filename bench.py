@@ -36,7 +36,10 @@ UNIT = "images*keypoints/s"
 WORKLOAD = "cfg2"
 HN = 512
 THRESH = 0.99
-KERNELS_PER_STEP = 6   # mask_bits, select_scan, gather, generate, vote, refit
+KERNELS_PER_STEP = 6   # mask_bits, thin_scan, gather, generate, vote, refit
+# dram__bytes_read.sum + dram__bytes_write.sum of one vote_kernel launch on this workload, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_summary.txt): 39 394 304 + 256 bytes
+VOTE_KERNEL_DRAM_BYTES = 39394560
 
 
 def _env_int(name, default):
@@ -294,14 +297,18 @@ def run_ours(args):
             "gpu_launches": KERNELS_PER_STEP * args.steps,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (achieved / hbm_peak) if achieved else None, "traffic": args.traffic,
-                "kernel": "pvb::vote_kernel<4,128>", "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
+                "frac": (achieved / hbm_peak) if achieved else None,
+                "traffic": args.traffic if args.traffic is not None else VOTE_KERNEL_DRAM_BYTES,
+                "kernel": "pvb::vote_kernel<4,128,8,512>", "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
                 "peak_source": peak_src,
                 "note": "the vote kernel is FP32-issue bound by construction (hn inlier tests per 16 loaded bytes); "
                         "see 'alu' and DESIGN.md",
             },
             "alu": {"inlier_tests_per_step": tests, "tests_per_s_vote_kernel": tests / (vote_ms * 1e-3) if vote_ms else None,
-                    "lane_ops_peak_per_s": 148 * 128 * sm_mhz * 1e6},
+                    "lane_ops_peak_per_s": 148 * 128 * sm_mhz * 1e6,
+                    "sass_instr_per_test": 7.1,
+                    "note": "454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
+                            "24 LDS); tools/microbench.cu bounds this mix at 610 cycles/block/SMSP => ~4.2 T tests/s"},
             "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -79,6 +79,8 @@ def load():
             fn.restype = res
             fn.argtypes = args
         _LIB = lib
+        if os.environ.get("PVB_VOTE_VARIANT"):     # tooling: A/B the vote-kernel launch shapes
+            check(lib.pvb_set_tuning(0, int(os.environ["PVB_VOTE_VARIANT"])))
     return _LIB
 
 

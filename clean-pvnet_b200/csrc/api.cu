@@ -159,7 +159,7 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     VoteArgs &v = P->v;
     v.B = d->B; v.K = d->K; v.hn = d->hn; v.cap = L.capacity; v.W = d->W; v.H = d->H;
     v.thresh = d->inlier_thresh;
-    v.tn = s.tn; v.state = s.state; v.xy = s.xy; v.cmax_dev = nullptr; v.ox = 0.f; v.oy = 0.f;
+    v.tn = s.tn; v.state = s.state; v.xy = s.xy;
     v.dirs = s.dirs; v.idxs = idxs; v.seed = d->seed;
     v.tag_idx = d->rng_tag_idx ? (uint32_t)d->rng_tag_idx : tag_idx;
     v.img_base = d->img_base;
@@ -381,7 +381,7 @@ PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK;
 
 PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant)
 {
-    if (vote_variant < 0 || vote_variant > 5) return fail(PVB_ERR_INVALID, "vote_variant must be 0..5");
+    if (vote_variant < 0 || vote_variant > 2) return fail(PVB_ERR_INVALID, "vote_variant must be 0..2");
     set_vote_tuning(vote_chunk, vote_variant);
     return PVB_OK;
 }
@@ -500,8 +500,8 @@ PVB_API int pvb_vote_count(const float *direct, const float *coords, const float
     VoteArgs v;
     memset(&v, 0, sizeof(v));
     v.B = 1; v.K = vn; v.hn = hn; v.cap = tn; v.W = 0; v.H = 0; v.thresh = inlier_thresh;
-    v.tn = meta; v.state = meta + 1; v.xy = xy; v.cmax_dev = reinterpret_cast<const float *>(meta + 2);
-    v.ox = 0.f; v.oy = 0.f; v.dirs = dirs; v.idxs = nullptr; v.hyp = hyp_k; v.counts = counts_k;
+    v.tn = meta; v.state = meta + 1; v.xy = xy;
+    v.dirs = dirs; v.idxs = nullptr; v.hyp = hyp_k; v.counts = counts_k;
     e = launch_vote(v, st);
     if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
     e = launch_compat_unpack_counts(counts_k, counts, vn, hn, st);

@@ -90,9 +90,7 @@ __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffff
 // Parameters of the cone test used by the fast path of the vote kernel (vote.cu).
 struct ConeParams {
     float kappa;   // tan(acos(thresh)) = sqrt(1-t^2)/t
-    float band;    // guard band per unit of S = |hx-ox|+|hy-oy|+cmax ; +inf => exact path only
-    float ox, oy;  // coordinate origin (image centre) used by the fast path
-    float cmax;    // max over pixels of |cx-ox|+|cy-oy|
+    float band;    // guard band per unit of S = |hx-ox|+|hy-oy|+cmax(tile) ; +inf => exact path only
     float thresh;  // (float)inlier_thresh
 };
 

@@ -118,8 +118,6 @@ compat_repack_kernel(const float *__restrict__ direct, const float *__restrict__
         xy[i] = c;
         for (int k = 0; k < vn; ++k)
             dirs[(size_t)k * tn + i] = make_float2(direct[((size_t)i * vn + k) * 2], direct[((size_t)i * vn + k) * 2 + 1]);
-        // max |cx|+|cy| as float bits (monotone for non-negative floats; NaN/inf sort above every finite value)
-        atomicMax(reinterpret_cast<unsigned int *>(meta + 2), __float_as_uint(fabsf(c.x) + fabsf(c.y)));
     }
     if (i < hn)
         for (int k = 0; k < vn; ++k)

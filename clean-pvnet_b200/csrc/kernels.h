@@ -30,8 +30,6 @@ struct VoteArgs {
     const int *tn;        // [B]
     const int *state;     // [B]
     const float2 *xy;     // [B][cap]   pixel coordinates (x,y)
-    const float *cmax_dev; // optional device scalar: max |cx-ox|+|cy-oy| (else derived from W,H)
-    float ox, oy;         // fast-path origin
     const float2 *dirs;   // [B][K][cap]
     const int32_t *idxs;  // optional [B][hn][K][2]
     uint64_t seed;
@@ -60,7 +58,7 @@ cudaError_t launch_compat_generate(const float *direct, const float *coords, con
 cudaError_t launch_compat_vote(const float *direct, const float *coords, const float *hyp, uint8_t *inliers,
                                int tn, int vn, int hn, float thresh, bool vanishing, cudaStream_t st);
 // reference layout -> layer layout (pix/dirs/hyp in k-major) for pvb_vote_count
-// meta: int[4] = { tn, state(0), float bits of max(|cx|+|cy|), unused }
+// meta: int[4] = { tn, state(0), unused, unused }
 cudaError_t launch_compat_repack(const float *direct, const float *coords, const float *hyp, int tn, int vn,
                                  int hn, float2 *dirs, float2 *xy, float2 *hyp_k, int *meta, cudaStream_t st);
 cudaError_t launch_compat_unpack_counts(const int *counts_k, int *counts, int vn, int hn, cudaStream_t st);

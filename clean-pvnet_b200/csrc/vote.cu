@@ -69,10 +69,9 @@ cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st)
 struct VoteK {
     VoteArgs a;
     ConeParams cone;
-    int chunk;     // pixels per CTA (multiple of VOTE_TILE)
+    int chunk;     // unused
 };
 
-constexpr int VOTE_TILE = 256;    // pixels per CTA, staged in shared memory
 constexpr int VOTE_BLOCK = 16;    // pixels per unrolled block (one guard-band check per block)
 
 __device__ __forceinline__ float4 lds128(uint32_t addr)
@@ -92,7 +91,7 @@ __device__ __forceinline__ float cone_margin(const float4 ra, const float2 rb, f
     return ap - fabsf(pp);
 }
 
-template <int HPT, int NT, int MINB>
+template <int HPT, int NT, int MINB, int VOTE_TILE>
 __global__ void __launch_bounds__(NT, MINB)
 vote_kernel(const VoteK p)
 {
@@ -211,27 +210,37 @@ vote_kernel(const VoteK p)
         bool flag = false;
 #pragma unroll
         for (int j = 0; j < HPT; ++j) flag |= mn[j] < dl[j];
-        if (flag) {
-            // rare: a margin of this block lies inside the guard band -> redo exactly those tests with the
-            // reference's operation sequence and correct the tally (fast verdict = sign bit of m)
+        if (__any_sync(0xffffffffu, flag)) {
+            // rare, warp-cooperative: for every (lane, j) whose block has a margin inside the guard band, 16 lanes
+            // re-test one pixel each against that hypothesis with the reference's exact operation sequence; the
+            // reduced correction goes back to the owning lane (fast verdict = sign bit of m)
             const int nb = min(VOTE_BLOCK, n - i0);      // padding stays "not an inlier"
-            for (int u = 0; u < nb; ++u) {
-                const int i = i0 + u;
-                const float4 ra = s_a[i];
-                const float2 rb = s_b[i];
+            float4 ra = make_float4(0.f, 0.f, -1e30f, 0.f);
+            float2 rb = make_float2(0.f, 0.f), vv = make_float2(0.f, 0.f), cc = make_float2(0.f, 0.f);
+            if (lane < nb) {
+                ra = s_a[i0 + lane]; rb = s_b[i0 + lane];
+                vv = __ldg(dk + i0 + lane); cc = __ldg(xy + i0 + lane);
+            }
 #pragma unroll
-                for (int j = 0; j < HPT; ++j) {
-                    if (mn[j] < dl[j]) {
-                        const float m = cone_margin(ra, rb, hxc[j], hyc[j]);
-                        if (fabsf(m) < dl[j]) {
-                            const int h = hbase + j * NT;
-                            const float2 q = (h < a.hn) ? hyp[h] : make_float2(0.f, 0.f);
-                            const float2 vv = __ldg(dk + i);
-                            const float2 cc = __ldg(xy + i);
+            for (int j = 0; j < HPT; ++j) {
+                unsigned bm = __ballot_sync(0xffffffffu, mn[j] < dl[j]);
+                while (bm) {
+                    const int L = __ffs(bm) - 1;
+                    bm &= bm - 1;
+                    const float hx_ = __shfl_sync(0xffffffffu, hxc[j], L), hy_ = __shfl_sync(0xffffffffu, hyc[j], L);
+                    const float dl_ = __shfl_sync(0xffffffffu, dl[j], L);
+                    const int h = hbase - lane + L + j * NT;
+                    const float2 q = (h < a.hn) ? __ldg(hyp + h) : make_float2(0.f, 0.f);
+                    int delta = 0;
+                    if (lane < nb) {
+                        const float m = cone_margin(ra, rb, hx_, hy_);
+                        if (fabsf(m) < dl_) {
                             const bool in = vote_exact(vv.x, vv.y, cc.x, cc.y, q.x, q.y, thresh);
-                            neg[j] += (in ? 0 : 1) - (int)(__float_as_uint(m) >> 31);
+                            delta = (in ? 0 : 1) - (int)(__float_as_uint(m) >> 31);
                         }
                     }
+                    delta = __reduce_add_sync(0xffffffffu, delta);
+                    if (lane == L) neg[j] += delta;
                 }
             }
         }
@@ -255,7 +264,6 @@ ConeParams make_cone(float thresh)
 {
     ConeParams c;
     c.thresh = thresh;
-    c.ox = c.oy = c.cmax = 0.f;   // the origin is chosen per pixel tile inside the kernel
     const double t = (double)thresh;
     if (t > 0.0 && t < 1.0) {
         const double s = sqrt(1.0 - t * t);
@@ -285,22 +293,18 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
     VoteK p;
     p.a = a;
     p.cone = make_cone(a.thresh);
-    p.chunk = VOTE_TILE;
-    const int chunks = (a.cap + VOTE_TILE - 1) / VOTE_TILE;
-#define PVB_VOTE(HPT, NT, MINB)                                                         \
+    p.chunk = 0;
+#define PVB_VOTE(HPT, NT, MINB, TILE)                                                   \
     do {                                                                                \
         const int slices = (a.hn + (HPT) * (NT) - 1) / ((HPT) * (NT));                  \
-        dim3 g(chunks, a.K * slices, a.B);                                              \
-        vote_kernel<HPT, NT, MINB><<<g, NT, 0, st>>>(p);                                \
+        dim3 g((a.cap + (TILE) - 1) / (TILE), a.K * slices, a.B);                       \
+        vote_kernel<HPT, NT, MINB, TILE><<<g, NT, 0, st>>>(p);                          \
     } while (0)
-    if (a.hn <= 128) PVB_VOTE(1, 128, 1);
-    else if (a.hn <= 256) PVB_VOTE(2, 128, 1);
-    else if (g_vote_variant == 1) PVB_VOTE(8, 64, 1);
-    else if (g_vote_variant == 2) PVB_VOTE(4, 128, 10);
-    else if (g_vote_variant == 5) PVB_VOTE(4, 128, 1);
-    else if (g_vote_variant == 3) PVB_VOTE(4, 128, 12);
-    else if (g_vote_variant == 4) PVB_VOTE(8, 64, 16);
-    else PVB_VOTE(4, 128, 8);
+    if (a.hn <= 128) PVB_VOTE(1, 128, 1, 256);
+    else if (a.hn <= 256) PVB_VOTE(2, 128, 1, 256);
+    else if (g_vote_variant == 1) PVB_VOTE(4, 128, 8, 256);
+    else if (g_vote_variant == 2) PVB_VOTE(4, 128, 8, 1024);
+    else PVB_VOTE(4, 128, 8, 512);     // measured best on B200 (profiles/r01_vote_tuning.md)
 #undef PVB_VOTE
     return cudaGetLastError();
 }

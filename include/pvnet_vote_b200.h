@@ -172,8 +172,8 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
 /* Launch-shape tuning of the vote kernel (tooling; process-wide).  vote_chunk: pixels per CTA (multiple
- * of 256, <=0 keeps the current value); vote_variant: 0 = 4 hypotheses/thread x 128 threads,
- * 1 = 8 hypotheses/thread x 64 threads.  Results do not depend on either. */
+ * of 256, <=0 keeps the current value; currently ignored); vote_variant: pixel-tile size per CTA,
+ * 0 = 512 (default), 1 = 256, 2 = 1024.  Results do not depend on either. */
 PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);
 PVB_API int pvb_profile_read(double *ms, int32_t n);

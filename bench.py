@@ -246,6 +246,28 @@ def run_ours(args):
     ms_per_step = ms_max / args.steps
     value = total * K / (ms_per_step * 1e-3)
 
+    # ---- extras (context, not the headline): the un_pnp production pair (resnet18.py:71-72) and B=1 latency
+    extras = {}
+    try:
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / n
+        mean = out[rank * B:(rank + 1) * B] if world > 1 else out
+        extras["estimate_voting_distribution_ms"] = timed(
+            lambda: pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, seed=7, img_base=rank * B), 10)
+        extras["v3_latency_b1_ms"] = timed(
+            lambda: pvb.ransac_voting_layer_v3(mask[:1], vertex[:1], HN, inlier_thresh=THRESH, seed=7), 50)
+    except Exception as e:
+        extras["error"] = str(e)
+
     # ---- end-to-end: pinned host inputs -> H2D -> kernels -> D2H, through the public host entry
     mh, vh = mask.cpu().pin_memory(), vertex.contiguous().cpu().pin_memory()
     oh = torch.empty((B, K, 2), dtype=torch.float32).pin_memory()
@@ -310,6 +332,7 @@ def run_ours(args):
                     "note": "454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
                             "24 LDS); tools/microbench.cu bounds this mix at 610 cycles/block/SMSP => ~4.2 T tests/s"},
             "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
+            "extras": extras,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -90,7 +90,7 @@ int make_layout(const pvb_desc *d, pvb_layout *L)
     if (rc) return rc;
     const size_t B = (size_t)d->B, K = (size_t)d->K, hn = (size_t)d->hn;
     const int nwords = (int)(((long long)d->H * d->W + 31) / 32);
-    const int nblocks = (nwords + 255) / 256;
+    const int nblocks = (nwords + 127) / 128;      // == TS_THREADS of select.cu
     const int cap = default_capacity(d);
     const int splits = refit_splits_for(cap);
     size_t off = 0;
@@ -382,7 +382,8 @@ PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK;
 PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant)
 {
     if (vote_variant < 0 || vote_variant > 2) return fail(PVB_ERR_INVALID, "vote_variant must be 0..2");
-    set_vote_tuning(vote_chunk, vote_variant);
+    (void)vote_chunk;
+    set_vote_tuning(vote_variant);
     return PVB_OK;
 }
 

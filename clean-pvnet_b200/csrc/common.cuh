@@ -69,9 +69,9 @@ __device__ __forceinline__ bool vote_exact(float vx, float vy, float cx, float c
     return __fdiv_rn(dot, den) > thresh;
 }
 
-// (double)n < 1e-6 for a float n, without the F2F: floats below 1e-6 are exactly those
-// <= float(1e-6) = 0x358637BD (9.99999997e-07 < 1e-6 < next float).
-__device__ __forceinline__ bool norm_below_1e6(float n) { return n <= __int_as_float(0x358637BD); }
+// Largest float below 1e-6: (double)n < 1e-6  <=>  n <= below_1e6() for a float n
+// (float(1e-6) = 0x358637BD = 9.99999997e-07 < 1e-6 < next float).
+__device__ __forceinline__ float below_1e6() { return __int_as_float(0x358637BD); }
 
 __device__ __forceinline__ float warp_sum(float v)
 {

@@ -42,7 +42,7 @@ struct VoteArgs {
 cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st);
 // counts[b][k][h] = #pixels voting for hyp[b][k][h]   (zeroes counts itself)
 cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st);
-void set_vote_tuning(int chunk, int variant);   // tooling: pixels per CTA, hypotheses-per-thread variant
+void set_vote_tuning(int variant);   // tooling: pixel-tile size per CTA
 // argmax + winner refit -> out_kpt [B][K][2], win [B][K].  The pixels of one (image,keypoint) are split
 // over `splits` CTAs; partial normal equations meet in `partial`, the last CTA to arrive (ticket) adds
 // them in a fixed order and solves, so the result is deterministic.

@@ -6,8 +6,8 @@
 //
 // HBM layout produced (see pvb_layout in include/pvnet_vote_b200.h):
 //   bits    uint32[B][nwords]      1 bit per pixel, row-major
-//   wordoff int32 [B][nwords]      exclusive popcount prefix inside each 256-word block
-//   blocktot int32[B][nblocks]     selected pixels per 256-word block  -> order-preserving compaction
+//   wordoff int32 [B][nwords]      exclusive popcount prefix inside each 128-word block
+//   blocktot int32[B][nblocks]     selected pixels per 128-word block  -> order-preserving compaction
 //   xy      float2[B][cap]         (x,y) of the t-th selected pixel (torch.nonzero order, :140-141)
 //   dirs    float2[B][K][cap]      vertex vectors of the selected pixels, keypoint-major so that a
 //                                  (image,keypoint) vote CTA streams one contiguous float2 array
@@ -29,11 +29,13 @@ __device__ __forceinline__ uint32_t mask_byte<double>(double v) { return (uint32
 
 constexpr int MB_WARPS = 8;
 constexpr int MB_UNROLL = 8;
+constexpr int MB_WORDS = 16;     // bitmap words (of 32 pixels) per warp: 2 rounds of 8 loads in flight per lane
 
-// One warp converts 1024 pixels into 32 bitmap words with coalesced loads (lane = pixel within
-// word) and ballots; lane i keeps word i so the 32 words leave as one coalesced store.  Loads are
-// issued MB_UNROLL at a time before any ballot so that each warp keeps 2 KB (int64 masks) in flight.
-template <typename T, int MODE>
+// One warp converts 512 pixels into 16 bitmap words with coalesced loads (lane = pixel within
+// word) and ballots; lane i keeps word i so the words leave as one coalesced store.  Loads are
+// issued MB_UNROLL at a time before any ballot so that each warp keeps 2 KB (int64 masks) in flight;
+// 16 words per warp gives a full wave of 64 resident warps per SM at 480x640 x 16 images.
+template <typename T, int MODE, bool CONTIG>
 __global__ void __launch_bounds__(MB_WARPS * 32)
 mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long long sx, int H, int W,
                  int nwords, uint32_t *__restrict__ bits, unsigned long long *__restrict__ fgsum,
@@ -41,22 +43,30 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
 {
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w0 = (blockIdx.x * MB_WARPS + warp) * 32;
+    const int w0 = (blockIdx.x * MB_WARPS + warp) * MB_WORDS;
     if (w0 >= nwords) return;
     const int HW = H * W;
     const T *mb = mask + (long long)b * sb;
-    const bool contig = (sx == 1 && sy == W);
+    // fast path: contiguous image and all MB_WORDS*32 pixels of this warp in range -> no per-element address
+    // arithmetic or bounds test between the loads
+    const bool full = CONTIG && ((w0 + MB_WORDS) * 32 <= HW);
     uint32_t myword = 0, sum = 0;
-    for (int i0 = 0; i0 < 32; i0 += MB_UNROLL) {
+    for (int i0 = 0; i0 < MB_WORDS; i0 += MB_UNROLL) {
         T v[MB_UNROLL];
+        if (full) {
+            const T *q = mb + (size_t)(w0 + i0) * 32 + lane;
 #pragma unroll
-        for (int u = 0; u < MB_UNROLL; ++u) {
-            const int p = (w0 + i0 + u) * 32 + lane;
-            v[u] = (T)0;
-            if (p < HW) {
-                long long off = p;
-                if (!contig) { const int y = p / W; off = (long long)y * sy + (long long)(p - y * W) * sx; }
-                v[u] = __ldg(mb + off);
+            for (int u = 0; u < MB_UNROLL; ++u) v[u] = __ldg(q + u * 32);
+        } else {
+#pragma unroll
+            for (int u = 0; u < MB_UNROLL; ++u) {
+                const int p = (w0 + i0 + u) * 32 + lane;
+                v[u] = (T)0;
+                if (p < HW) {
+                    long long off = p;
+                    if (!CONTIG) { const int y = p / W; off = (long long)y * sy + (long long)(p - y * W) * sx; }
+                    v[u] = __ldg(mb + off);
+                }
             }
         }
 #pragma unroll
@@ -70,7 +80,7 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
             sum += val;
         }
     }
-    if (w0 + lane < nwords) bits[(size_t)b * nwords + w0 + lane] = myword;
+    if (lane < MB_WORDS && w0 + lane < nwords) bits[(size_t)b * nwords + w0 + lane] = myword;
     const int s = warp_sum((int)sum);
     const int c = warp_sum(__popc(myword));
     if (lane == 0) {
@@ -79,10 +89,10 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
     }
 }
 
-// One CTA per 256 bitmap words: decides skip / thinning for its image (ransac_voting_gpu.py:129-138),
+// One CTA per 128 bitmap words: decides skip / thinning for its image (ransac_voting_gpu.py:129-138),
 // applies the Bernoulli thinning to its words, and writes the exclusive popcount prefix WITHIN the
 // block plus the block total; the gather kernel adds the totals of the preceding blocks.
-constexpr int TS_THREADS = 256;
+constexpr int TS_THREADS = 128;
 
 __global__ void __launch_bounds__(TS_THREADS)
 thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__restrict__ blocktot,
@@ -152,7 +162,7 @@ thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__
     }
 }
 
-// One CTA per 256-word block (the thin_scan granularity).  The block's selected pixels are first
+// One CTA per 128-word block (the thin_scan granularity).  The block's selected pixels are first
 // listed in shared memory (position = the in-block prefix thin_scan left in wordoff[]), then the CTA
 // walks that dense list: every lane is active, loads touch only selected pixels, and each store
 // instruction of a warp writes 32 consecutive t of one keypoint plane of dirs[] (256 B).
@@ -165,7 +175,7 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
               long long sB, long long sH, long long sW, long long sK, long long sC,
               float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W)
 {
-    __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (13 bits)
+    __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (12 bits)
     __shared__ int s_base;
     const int b = blockIdx.y, blk = blockIdx.x;
     if (state[b] != 0) return;
@@ -223,16 +233,22 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
 cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
 {
     const int nwords = a.nwords;
-    dim3 g1((nwords + MB_WARPS * 32 - 1) / (MB_WARPS * 32), a.B);
-#define PVB_MB(T)                                                                                        \
+    dim3 g1((nwords + MB_WARPS * MB_WORDS - 1) / (MB_WARPS * MB_WORDS), a.B);
+#define PVB_MB2(T, MODE)                                                                                 \
     do {                                                                                                 \
-        if (a.select_mode == PVB_SELECT_BYTE)                                                            \
-            mask_bits_kernel<T, PVB_SELECT_BYTE><<<g1, MB_WARPS * 32, 0, st>>>(                           \
+        if (contig)                                                                                      \
+            mask_bits_kernel<T, MODE, true><<<g1, MB_WARPS * 32, 0, st>>>(                                \
                 (const T *)a.mask, a.msb, a.msy, a.msx, a.H, a.W, nwords, a.bits, a.fgsum, a.nz);        \
         else                                                                                             \
-            mask_bits_kernel<T, PVB_SELECT_EQ1><<<g1, MB_WARPS * 32, 0, st>>>(                            \
+            mask_bits_kernel<T, MODE, false><<<g1, MB_WARPS * 32, 0, st>>>(                               \
                 (const T *)a.mask, a.msb, a.msy, a.msx, a.H, a.W, nwords, a.bits, a.fgsum, a.nz);        \
     } while (0)
+#define PVB_MB(T)                                                                                        \
+    do {                                                                                                 \
+        if (a.select_mode == PVB_SELECT_BYTE) PVB_MB2(T, PVB_SELECT_BYTE);                               \
+        else PVB_MB2(T, PVB_SELECT_EQ1);                                                                 \
+    } while (0)
+    const bool contig = (a.msx == 1 && a.msy == a.W);
     switch (a.mask_dtype) {
     case PVB_MASK_U8: PVB_MB(uint8_t); break;
     case PVB_MASK_I8: PVB_MB(int8_t); break;
@@ -244,6 +260,7 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
     default: return cudaErrorInvalidValue;
     }
 #undef PVB_MB
+#undef PVB_MB2
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 g2(a.nblocks, a.B);

@@ -69,7 +69,6 @@ cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st)
 struct VoteK {
     VoteArgs a;
     ConeParams cone;
-    int chunk;     // unused
 };
 
 constexpr int VOTE_BLOCK = 16;    // pixels per unrolled block (one guard-band check per block)
@@ -154,7 +153,7 @@ vote_kernel(const VoteK p)
             if (i < n) {
                 const float n1 = __fsqrt_rn(__fmaf_rn(v[r].x, v[r].x, __fmul_rn(v[r].y, v[r].y)));   // the reference's norm1
                 const float cxc = c[r].x - ox, cyc = c[r].y - oy;
-                if (!(n1 > __int_as_float(0x358637BD))) {
+                if (!(n1 > below_1e6())) {
                     // (double)norm1 < 1e-6 or NaN: the reference never votes for this pixel (.cu:121)
                 } else if (!(n1 < 1e18f) || !(fabsf(cxc) + fabsf(cyc) <= cmax)) {
                     // outside the domain of the error analysis: force the exact path (m == 0 < delta)
@@ -278,13 +277,9 @@ ConeParams make_cone(float thresh)
     return c;
 }
 
-static int g_vote_variant = 0;      // 0: 4 hyps/thread x 128 threads, 1: 8 hyps/thread x 64 threads
+static int g_vote_variant = 0;      // pixel-tile size per CTA: 0 -> 512 (default), 1 -> 256, 2 -> 1024
 
-void set_vote_tuning(int chunk, int variant)
-{
-    (void)chunk;   // one 256-pixel tile per CTA (tile-local origin); kept for ABI stability
-    g_vote_variant = variant;
-}
+void set_vote_tuning(int variant) { g_vote_variant = variant; }
 
 cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
 {
@@ -293,7 +288,6 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
     VoteK p;
     p.a = a;
     p.cone = make_cone(a.thresh);
-    p.chunk = 0;
 #define PVB_VOTE(HPT, NT, MINB, TILE)                                                   \
     do {                                                                                \
         const int slices = (a.hn + (HPT) * (NT) - 1) / ((HPT) * (NT));                  \

@@ -101,8 +101,8 @@ typedef struct pvb_layout {
     size_t tn;       /* int32[B]   selected pixel count after thinning (0 when skipped) */
     size_t state;    /* int32[B]   0 ok, 1 skipped (fg < min_num) */
     size_t bits;     /* uint32[B][nwords] selection bitmap, bit j of word w = pixel 32*w+j */
-    size_t wordoff;  /* int32[B][nwords]  exclusive prefix of popcounts inside each 256-word block */
-    size_t blocktot; /* int32[B][nblocks] selected pixels per 256-word block */
+    size_t wordoff;  /* int32[B][nwords]  exclusive prefix of popcounts inside each 128-word block */
+    size_t blocktot; /* int32[B][nblocks] selected pixels per 128-word block */
     size_t xy;       /* float2[B][capacity]   (x,y) of the t-th selected pixel, row-major (torch.nonzero) order */
     size_t dirs;     /* float2[B][K][capacity] gathered vertex vectors (k-major) */
     size_t hyp;      /* float2[B][K][hn] */
@@ -111,7 +111,7 @@ typedef struct pvb_layout {
     size_t refit_partial; /* double[B][K][refit_splits][5] partial normal equations */
     size_t refit_ticket;  /* int32[B][K] arrival counters of the refit CTAs */
     int32_t nwords;  /* ceil(H*W/32) */
-    int32_t nblocks; /* ceil(nwords/256) */
+    int32_t nblocks; /* ceil(nwords/128) */
     int32_t capacity;
     int32_t refit_splits;
 } pvb_layout;

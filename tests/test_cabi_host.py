@@ -140,3 +140,11 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pvnet_oracle" not in text and "oracle/" not in text.replace("see oracle/", ""), f
+
+
+def test_missing_library_fails_loudly(pvb, monkeypatch):
+    """No CPU / PyTorch fallback: without the CUDA library the product raises, it never degrades."""
+    monkeypatch.setattr(pvb._lib, "_LIB", None)
+    monkeypatch.setattr(pvb._lib, "LIB_PATH", "/nonexistent/libpvnet_vote_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
+        pvb._lib.load()

@@ -196,6 +196,21 @@ def test_error_paths(pvb):
         pvb.ransac_voting_layer_v3(big, vertex, 32, max_num=100, selection=sel, capacity=256, debug=True)
 
 
+def test_empty_batch_and_empty_foreground(pvb):
+    mask, vertex, _ = _inputs(pvb, "tiny", seed=17)
+    out = pvb.ransac_voting_layer_v3(mask[:0], vertex[:0], 32, inlier_thresh=0.99)
+    assert out.shape == (0, vertex.shape[3], 2)
+    _, cov = pvb.estimate_voting_distribution_with_mean(mask[:0], vertex[:0], out)
+    assert cov.shape == (0, vertex.shape[3], 2, 2)
+    zero = torch.zeros_like(mask)
+    out = pvb.ransac_voting_layer_v3(zero, vertex, 32, inlier_thresh=0.99)
+    assert (out == 0).all()                          # every image skipped (:129-132)
+    one_px = zero.clone()
+    one_px[:, 5, 5] = 1
+    out = pvb.ransac_voting_layer_v3(one_px, vertex, 32, inlier_thresh=0.99, min_num=1)
+    assert torch.isfinite(out).all()                 # tn == 1: every pair is degenerate -> hypotheses (0,0)
+
+
 def test_host_buffer_entry_matches_device_entry(pvb):
     mask, vertex, _ = _inputs(pvb, "small", seed=16, B=5)
     dev = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, seed=21, max_num=700)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "pvb_read_status": (ctypes.c_int, [_dp, _vp, _vp]),
     "pvb_host_scratch_bytes": (_sz, [_dp, _i32]),
     "pvb_ransac_voting_v3_host": (ctypes.c_int, [_dp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "pvb_set_host_mode": (ctypes.c_int, [_i32]),
     "pvb_profile_enable": (ctypes.c_int, [_i32]),
     "pvb_profile_reset": (ctypes.c_int, []),
     "pvb_set_tuning": (ctypes.c_int, [_i32, _i32]),

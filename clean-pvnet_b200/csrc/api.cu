@@ -31,6 +31,7 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 // ---- stage timing (pvb_profile_*) --------------------------------------------------------
 struct ProfCall { cudaEvent_t ev[PVB_STAGE_COUNT + 1]; };
 thread_local bool g_prof_on = false;
+bool g_host_zero_copy = true;      // pvb_set_host_mode(): read pinned host inputs in place over PCIe
 thread_local std::vector<ProfCall> g_prof_calls;
 thread_local std::vector<cudaEvent_t> g_prof_pool;
 
@@ -146,6 +147,7 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     s.B = d->B; s.H = d->H; s.W = d->W; s.K = d->K; s.nwords = L.nwords; s.nblocks = L.nblocks; s.cap = L.capacity;
     s.min_num = d->min_num; s.max_num = d->max_num; s.img_base = d->img_base;
     s.seed = d->seed; s.tag_sel = d->rng_tag_sel ? (uint32_t)d->rng_tag_sel : tag_sel;
+    s.rowwise_gather = 0;
     s.bits = reinterpret_cast<uint32_t *>(w + L.bits);
     s.wordoff = reinterpret_cast<int *>(w + L.wordoff);
     s.blocktot = reinterpret_cast<int *>(w + L.blocktot);
@@ -172,15 +174,22 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     return PVB_OK;
 }
 
-int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
+int run_select(const Plan &P, cudaStream_t st)
 {
     // status, fgsum, nz, tn, state, refit tickets: contiguous at the start of the workspace
     cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.bits, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(header)");
     e = launch_select(P.s, st);
     if (e != cudaSuccess) return cuda_fail(e, "select kernels");
+    return PVB_OK;
+}
+
+int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
+{
+    int rc = run_select(P, st);
+    if (rc) return rc;
     prof_mark(pc, PVB_STAGE_SELECT, st);
-    e = launch_generate(P.v, st);
+    cudaError_t e = launch_generate(P.v, st);
     if (e != cudaSuccess) return cuda_fail(e, "generate kernel");
     prof_mark(pc, PVB_STAGE_GENERATE, st);
     e = launch_vote(P.v, st);
@@ -317,30 +326,37 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
     if (rc) return rc;
     if (!dev_scratch || dev_scratch_bytes < 2 * S.end) return fail(PVB_ERR_WORKSPACE, "device scratch too small: need %zu", 2 * S.end);
     if (reinterpret_cast<uintptr_t>(dev_scratch) & 255u) return fail(PVB_ERR_WORKSPACE, "device scratch must be 256-byte aligned");
-    static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
-    static thread_local cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // Two-stage software pipeline over `chunk_images`-sized pieces, double-buffered in dev_scratch:
+    //   stage A (high-priority stream): bring the piece in -- staged H2D copies, or (zero-copy) let mask_bits and
+    //            gather read the pinned host tensors in place -- and run the select kernels;   PCIe-bound
+    //   stage B (low-priority stream):  generate, vote, refit, D2H of the keypoints;          SM-bound
+    // Stage A of piece i+1 overlaps stage B of piece i; the priority lets the bus-bound CTAs slip in as vote
+    // CTAs retire.
+    static thread_local cudaStream_t s_in = nullptr, s_cmp = nullptr;
+    static thread_local cudaEvent_t ev_user = nullptr, ev_sel[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr},
+                                    ev_end = nullptr;
     static thread_local int streams_dev = -1;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
     if (streams_dev != dev) {
-        for (int i = 0; i < 2; ++i) {
-            e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-        }
-        for (int i = 0; i < 3; ++i) {
-            e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least, hi = greatest priority (numerically lower)
+        e = cudaStreamCreateWithPriority(&s_in, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_cmp, cudaStreamNonBlocking, lo);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        cudaEvent_t *evs[] = {&ev_user, &ev_sel[0], &ev_sel[1], &ev_cmp[0], &ev_cmp[1], &ev_end};
+        for (cudaEvent_t *pe : evs) {
+            e = cudaEventCreateWithFlags(pe, cudaEventDisableTiming);
             if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
         }
         streams_dev = dev;
     }
     cudaStream_t user = static_cast<cudaStream_t>(stream);
-    e = cudaEventRecord(ev[2], user);
-    if (e != cudaSuccess) return cuda_fail(e, "event record");
-    for (int i = 0; i < 2; ++i) {
-        e = cudaStreamWaitEvent(streams[i], ev[2], 0);
-        if (e != cudaSuccess) return cuda_fail(e, "stream wait");
-    }
+    e = cudaEventRecord(ev_user, user);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_in, ev_user, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_cmp, ev_user, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "stream wait");
     const size_t HW = (size_t)d->H * d->W;
     const size_t mbytes = HW * mask_elt_bytes(d->mask_dtype), vbytes = HW * d->K * 2 * sizeof(float);
     const size_t obytes = (size_t)d->K * 2 * sizeof(float);
@@ -348,36 +364,69 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
     pvb_layout Lc;
     rc = make_layout(&dc, &Lc);
     if (rc) return rc;
-    int slot = 0;
-    for (int b0 = 0; b0 < d->B; b0 += chunk_images, slot ^= 1) {
+    // Zero-copy: when both inputs are pinned (device-mapped) host memory the kernels read them in place over
+    // PCIe -- the mask is streamed once by mask_bits, and gather fetches ONLY the selected pixels' rows
+    // (tn*K*8 bytes per image instead of the dense H*W*K*8), so the dense vertex field never crosses the bus.
+    bool zero_copy = g_host_zero_copy;
+    if (zero_copy) {
+        cudaPointerAttributes am, av;
+        if (cudaPointerGetAttributes(&am, mask_host) != cudaSuccess || cudaPointerGetAttributes(&av, vertex_host) != cudaSuccess ||
+            am.type != cudaMemoryTypeHost || av.type != cudaMemoryTypeHost || !am.devicePointer || !av.devicePointer) {
+            zero_copy = false;
+            cudaGetLastError();   // clear the sticky "invalid value" of an unregistered pointer
+        }
+    }
+    int slot = 0, piece = 0;
+    for (int b0 = 0; b0 < d->B; b0 += chunk_images, slot ^= 1, ++piece) {
         const int c = (d->B - b0 < chunk_images) ? d->B - b0 : chunk_images;
         char *sb = base + (size_t)slot * S.end;
-        cudaStream_t st = streams[slot];
-        e = cudaMemcpyAsync(sb + S.mask, static_cast<const char *>(mask_host) + (size_t)b0 * mbytes, (size_t)c * mbytes, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(sb + S.vertex, reinterpret_cast<const char *>(vertex_host) + (size_t)b0 * vbytes, (size_t)c * vbytes, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+        const void *mptr = sb + S.mask;
+        const float *vptr = reinterpret_cast<const float *>(sb + S.vertex);
+        // this slot's buffers are free once the piece that used them two steps ago has been computed
+        if (piece >= 2) {
+            e = cudaStreamWaitEvent(s_in, ev_cmp[slot], 0);
+            if (e != cudaSuccess) return cuda_fail(e, "stream wait");
+        }
+        if (zero_copy) {
+            mptr = static_cast<const char *>(mask_host) + (size_t)b0 * mbytes;
+            vptr = reinterpret_cast<const float *>(reinterpret_cast<const char *>(vertex_host) + (size_t)b0 * vbytes);
+        } else {
+            e = cudaMemcpyAsync(sb + S.mask, static_cast<const char *>(mask_host) + (size_t)b0 * mbytes, (size_t)c * mbytes, cudaMemcpyHostToDevice, s_in);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(sb + S.vertex, reinterpret_cast<const char *>(vertex_host) + (size_t)b0 * vbytes, (size_t)c * vbytes, cudaMemcpyHostToDevice, s_in);
+            if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+        }
         pvb_desc di = dc;
         di.B = c;
         di.img_base = d->img_base + b0;
         di.capacity = Lc.capacity;
-        rc = pvb_ransac_voting_v3(&di, sb + S.mask, reinterpret_cast<const float *>(sb + S.vertex), nullptr, nullptr,
-                                  reinterpret_cast<float *>(sb + S.out), sb + S.ws, S.end - S.ws, st);
+        Plan P;
+        rc = make_plan(&di, mptr, vptr, nullptr, nullptr, sb + S.ws, S.end - S.ws, 1u, 2u, &P);
         if (rc) return rc;
-        e = cudaMemcpyAsync(reinterpret_cast<char *>(out_kpt_host) + (size_t)b0 * obytes, sb + S.out, (size_t)c * obytes, cudaMemcpyDeviceToHost, st);
+        P.s.rowwise_gather = zero_copy ? 1 : 0;
+        rc = run_select(P, s_in);                                   // stage A
+        if (rc) return rc;
+        e = cudaEventRecord(ev_sel[slot], s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_cmp, ev_sel[slot], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "pipeline event");
+        e = launch_generate(P.v, s_cmp);                            // stage B
+        if (e == cudaSuccess) e = launch_vote(P.v, s_cmp);
+        if (e == cudaSuccess) e = launch_refit(P.v, P.win, P.refit, reinterpret_cast<float *>(sb + S.out), s_cmp);
+        if (e != cudaSuccess) return cuda_fail(e, "compute kernels");
+        e = cudaMemcpyAsync(reinterpret_cast<char *>(out_kpt_host) + (size_t)b0 * obytes, sb + S.out, (size_t)c * obytes, cudaMemcpyDeviceToHost, s_cmp);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_cmp[slot], s_cmp);
         if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
     }
-    for (int i = 0; i < 2; ++i) {
-        e = cudaEventRecord(ev[i], streams[i]);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ev[i], 0);
-        if (e != cudaSuccess) return cuda_fail(e, "join streams");
-    }
-    e = cudaStreamSynchronize(user);
+    e = cudaEventRecord(ev_end, s_cmp);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ev_end, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(user);
     if (e != cudaSuccess) return cuda_fail(e, "stream sync");
     return PVB_OK;
 }
 
 PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK; }
+
+PVB_API int pvb_set_host_mode(int32_t zero_copy) { g_host_zero_copy = zero_copy != 0; return PVB_OK; }
 
 PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant)
 {

@@ -14,6 +14,7 @@ struct SelectArgs {
     long long vs[5];              // vertex strides (elements)
     const float *selection;       // optional [B,H,W]
     int B, H, W, K, nwords, nblocks, cap, min_num, max_num, img_base;
+    int rowwise_gather;           // 1: vertex is zero-copy host memory, read whole pixel rows per warp
     uint64_t seed;
     uint32_t tag_sel;
     uint32_t *bits;

@@ -173,7 +173,8 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
               const int *__restrict__ blocktot, const int *__restrict__ state, int *__restrict__ tn,
               int *__restrict__ status, const float *__restrict__ vertex,
               long long sB, long long sH, long long sW, long long sK, long long sC,
-              float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W)
+              float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W,
+              int rowwise)
 {
     __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (12 bits)
     __shared__ int s_base;
@@ -209,6 +210,33 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
     const bool vec = (sC == 1 && (sK & 1) == 0 && (sW & 1) == 0 && (sH & 1) == 0 && (sB & 1) == 0 &&
                       (reinterpret_cast<uintptr_t>(vertex) & 7u) == 0);
     const float *vimg = vertex + (long long)b * sB;
+    if (rowwise && vec && sK == 2) {
+        // vertex lives in pinned HOST memory (zero-copy entry): consecutive lanes read consecutive float2 of
+        // the same pixel row so each selected pixel costs one contiguous 8*K-byte PCIe read, not K scattered ones
+        const int nel = min(total, max(cap - base, 0)) * K;
+        constexpr int U = 4;                       // PCIe reads in flight per thread
+        for (int e0 = tid; e0 < nel; e0 += GA_THREADS * U) {
+            float2 val[U];
+            int tt[U], kk[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * GA_THREADS;
+                tt[u] = -1;
+                if (e < nel) {
+                    const int i = e / K, k = e - i * K;
+                    const int p = blk * (TS_THREADS * 32) + (int)s_list[i];
+                    const int y = p / W, x = p - y * W;
+                    tt[u] = base + i; kk[u] = k;
+                    if (k == 0) xy[(size_t)b * cap + base + i] = make_float2((float)x, (float)y);
+                    val[u] = __ldg(reinterpret_cast<const float2 *>(vimg + (long long)y * sH + (long long)x * sW) + k);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (tt[u] >= 0) dirs[((size_t)b * K + kk[u]) * cap + tt[u]] = val[u];
+        }
+        return;
+    }
     for (int i = tid; i < total; i += GA_THREADS) {
         const int t = base + i;
         if (t >= cap) break;
@@ -273,7 +301,7 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
     dim3 g3(a.nblocks, a.B);
     gather_kernel<<<g3, GA_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
                                                 a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
-                                                a.nblocks, a.K, a.cap, a.W);
+                                                a.nblocks, a.K, a.cap, a.W, a.rowwise_gather);
     return cudaGetLastError();
 }
 

@@ -265,10 +265,12 @@ _host_scratch = {}
 
 def ransac_voting_layer_v3_host(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
                                 min_num=5, max_num=30000, *, device=None, chunk_images=2, seed=None, img_base=0,
-                                out=None):
-    """ransac_voting_layer_v3 for HOST tensors (ideally pinned): the C ABI's host-buffer entry
-    (pvb_ransac_voting_v3_host) streams the batch to the GPU in `chunk_images`-sized pieces on two
-    streams so copies overlap the kernels, and writes keypoints back to a host tensor."""
+                                out=None, zero_copy=True):
+    """ransac_voting_layer_v3 for HOST tensors: the C ABI's host-buffer entry (pvb_ransac_voting_v3_host)
+    processes the batch in `chunk_images`-sized pieces on two streams and writes keypoints to a host tensor.
+    With pinned inputs and zero_copy=True (default) the kernels read the inputs in place over PCIe: the mask
+    is streamed once and only the selected pixels' vertex rows cross the bus (tn*K*8 bytes per image instead
+    of the dense H*W*K*8).  Pageable inputs or zero_copy=False use staged cudaMemcpyAsync copies."""
     del confidence, max_iter
     if mask.is_cuda or vertex.is_cuda:
         raise RuntimeError("ransac_voting_layer_v3_host takes host tensors")
@@ -295,6 +297,7 @@ def ransac_voting_layer_v3_host(mask, vertex, round_hyp_num, inlier_thresh=0.999
         if sc is None or sc.numel() < nbytes:
             sc = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             _host_scratch[key] = sc
+        _lib.check(lib.pvb_set_host_mode(1 if zero_copy else 0))
         _lib.check(lib.pvb_ransac_voting_v3_host(d, mask.data_ptr(), vertex.data_ptr(), out.data_ptr(), chunk,
                                                  sc.data_ptr(), sc.numel(),
                                                  torch.cuda.current_stream(dev).cuda_stream))

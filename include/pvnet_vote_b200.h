@@ -151,12 +151,18 @@ PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream
 
 /* HOST-buffer variant of pvb_ransac_voting_v3: mask/vertex/out_kpt are host pointers
  * (pinned for full speed), contiguous [B,H,W] / [B,H,W,K,2] / [B,K,2].  Splits the batch into
- * `chunk_images`-sized pieces and overlaps the H2D copies with compute on two internal streams.
+ * `chunk_images`-sized pieces on two internal streams so that one piece's PCIe traffic overlaps the other's
+ * kernels; see pvb_set_host_mode for what crosses the bus.
  * Stream-ordered after the work already queued on `stream`; `stream` is synchronised before the
  * call returns (the result is in host memory), so CUDA events recorded on `stream` around the call
  * bracket all copies and kernels.  dev_scratch: 256-byte aligned device memory of
  * pvb_host_scratch_bytes(d, chunk_images) bytes. */
 PVB_API size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images);
+/* How the host entry moves its inputs (process-wide).  zero_copy != 0 (default): when mask_host and vertex_host
+ * are pinned, device-mapped host memory the kernels read them in place over PCIe -- the mask is streamed once and
+ * only the SELECTED pixels' vertex rows are fetched (tn*K*8 bytes per image instead of H*W*K*8).  Pageable
+ * inputs, or zero_copy == 0, take the staged path (cudaMemcpyAsync of both tensors, chunk by chunk). */
+PVB_API int pvb_set_host_mode(int32_t zero_copy);
 PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
                               float *out_kpt_host, int32_t chunk_images,
                               void *dev_scratch, size_t dev_scratch_bytes, pvb_stream_t stream);

@@ -133,6 +133,15 @@ def test_v3_hypothesis_counts(pvb, oracle, hn):
     _check_v3(pvb, oracle, mask, vertex, hn)
 
 
+@pytest.mark.parametrize("H,W,K", [(45, 61, 2), (33, 31, 1), (135, 180, 5), (7, 300, 3)])
+def test_v3_odd_image_sizes(pvb, oracle, H, W, K):
+    """H*W not a multiple of 32 (partial bitmap word), odd widths, single keypoint."""
+    cfg = dict(B=2, H=H, W=W, K=K, hn=40, fill=(0.3, 0.4), kind="blob")
+    mask, vertex, _ = _inputs(pvb, cfg, seed=H * 1000 + W)
+    _check_v3(pvb, oracle, mask, vertex, 40, max_num=200)
+    _check_v3(pvb, oracle, mask, vertex, 40)
+
+
 def test_v3_seed_follows_torch_manual_seed(pvb):
     mask, vertex, _ = _inputs(pvb, "tiny", seed=11)
     torch.manual_seed(5)

@@ -220,6 +220,40 @@ def test_empty_batch_and_empty_foreground(pvb):
     assert torch.isfinite(out).all()                 # tn == 1: every pair is degenerate -> hypotheses (0,0)
 
 
+def test_cuda_graph_capture_and_replay(pvb):
+    """The device entry points enqueue only (no sync, no allocation inside the library): one v3 +
+    distribution call is captured into a CUDA graph and replayed on new input values."""
+    mask, vertex, _ = _inputs(pvb, "small", seed=18)
+    static_mask, static_vertex = mask.clone(), vertex.clone()
+    want = pvb.ransac_voting_layer_v3(static_mask, static_vertex, 64, inlier_thresh=0.99, seed=9, max_num=800)
+    _, want_cov = pvb.estimate_voting_distribution_with_mean(static_mask, static_vertex, want, round_hyp_num=64,
+                                                             min_hyp_num=256, seed=10)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        # warm the per-stream workspace outside the capture
+        pvb.ransac_voting_layer_v3(static_mask, static_vertex, 64, inlier_thresh=0.99, seed=9, max_num=800)
+        pvb.estimate_voting_distribution_with_mean(static_mask, static_vertex, want, round_hyp_num=64, min_hyp_num=256, seed=10)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            out = pvb.ransac_voting_layer_v3(static_mask, static_vertex, 64, inlier_thresh=0.99, seed=9, max_num=800)
+            _, cov = pvb.estimate_voting_distribution_with_mean(static_mask, static_vertex, out, round_hyp_num=64,
+                                                                min_hyp_num=256, seed=10)
+    torch.cuda.current_stream().wait_stream(s)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want) and torch.equal(cov, want_cov)
+    # new data in the static buffers, replay only
+    mask2, vertex2, _ = _inputs(pvb, "small", seed=19)
+    static_mask.copy_(mask2); static_vertex.copy_(vertex2)
+    g.replay()
+    torch.cuda.synchronize()
+    want2 = pvb.ransac_voting_layer_v3(mask2, vertex2, 64, inlier_thresh=0.99, seed=9, max_num=800)
+    assert torch.equal(out, want2)
+
+
 def test_host_buffer_entry_matches_device_entry(pvb):
     mask, vertex, _ = _inputs(pvb, "small", seed=16, B=5)
     dev = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, seed=21, max_num=700)

@@ -29,7 +29,10 @@ int cuda_fail(cudaError_t e, const char *what)
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // ---- stage timing (pvb_profile_*) --------------------------------------------------------
-struct ProfCall { cudaEvent_t ev[PVB_STAGE_COUNT + 1]; };
+struct ProfCall {
+    cudaEvent_t start[PVB_STAGE_COUNT], end[PVB_STAGE_COUNT];   // per stage; stages may run on different streams
+    bool head;                                                   // first piece of an API call
+};
 thread_local bool g_prof_on = false;
 bool g_host_zero_copy = true;      // pvb_set_host_mode(): read pinned host inputs in place over PCIe
 thread_local std::vector<ProfCall> g_prof_calls;
@@ -43,20 +46,19 @@ cudaEvent_t prof_event()
     return e;
 }
 
-ProfCall *prof_begin(cudaStream_t st)
+ProfCall *prof_begin(bool head)
 {
     if (!g_prof_on) return nullptr;
     ProfCall pc;
-    for (auto &e : pc.ev) e = prof_event();
+    for (auto &e : pc.start) e = prof_event();
+    for (auto &e : pc.end) e = prof_event();
+    pc.head = head;
     g_prof_calls.push_back(pc);
-    cudaEventRecord(g_prof_calls.back().ev[0], st);
     return &g_prof_calls.back();
 }
 
-inline void prof_mark(ProfCall *pc, int stage, cudaStream_t st)
-{
-    if (pc) cudaEventRecord(pc->ev[stage + 1], st);
-}
+inline void prof_start(ProfCall *pc, int stage, cudaStream_t st) { if (pc) cudaEventRecord(pc->start[stage], st); }
+inline void prof_end(ProfCall *pc, int stage, cudaStream_t st) { if (pc) cudaEventRecord(pc->end[stage], st); }
 
 int default_capacity(const pvb_desc *d)
 {
@@ -186,16 +188,29 @@ int run_select(const Plan &P, cudaStream_t st)
 
 int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
 {
+    prof_start(pc, PVB_STAGE_SELECT, st);
     int rc = run_select(P, st);
     if (rc) return rc;
-    prof_mark(pc, PVB_STAGE_SELECT, st);
+    prof_end(pc, PVB_STAGE_SELECT, st);
+    prof_start(pc, PVB_STAGE_GENERATE, st);
     cudaError_t e = launch_generate(P.v, st);
     if (e != cudaSuccess) return cuda_fail(e, "generate kernel");
-    prof_mark(pc, PVB_STAGE_GENERATE, st);
+    prof_end(pc, PVB_STAGE_GENERATE, st);
+    prof_start(pc, PVB_STAGE_VOTE, st);
     e = launch_vote(P.v, st);
     if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
-    prof_mark(pc, PVB_STAGE_VOTE, st);
+    prof_end(pc, PVB_STAGE_VOTE, st);
     return PVB_OK;
+}
+
+size_t mask_elt_bytes(int dt)
+{
+    switch (dt) {
+    case PVB_MASK_U8: case PVB_MASK_I8: return 1;
+    case PVB_MASK_I16: return 2;
+    case PVB_MASK_I32: case PVB_MASK_F32: return 4;
+    default: return 8;
+    }
 }
 
 } // namespace
@@ -228,12 +243,13 @@ PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const floa
     if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
     if (d->B == 0) return PVB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ProfCall *pc = prof_begin(st);
+    ProfCall *pc = prof_begin(true);
     rc = run_front(P, st, pc);
     if (rc) return rc;
+    prof_start(pc, PVB_STAGE_FINISH, st);
     cudaError_t e = launch_refit(P.v, P.win, P.refit, out_kpt, st);
     if (e != cudaSuccess) return cuda_fail(e, "refit kernel");
-    prof_mark(pc, PVB_STAGE_FINISH, st);
+    prof_end(pc, PVB_STAGE_FINISH, st);
     return PVB_OK;
 }
 
@@ -247,12 +263,13 @@ PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask
     if (!mean || !out_cov) return fail(PVB_ERR_INVALID, "mean/out_cov is NULL");
     if (d->B == 0) return PVB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ProfCall *pc = prof_begin(st);
+    ProfCall *pc = prof_begin(true);
     rc = run_front(P, st, pc);
     if (rc) return rc;
+    prof_start(pc, PVB_STAGE_FINISH, st);
     cudaError_t e = launch_covariance(P.v, mean, out_cov, st);
     if (e != cudaSuccess) return cuda_fail(e, "covariance kernel");
-    prof_mark(pc, PVB_STAGE_FINISH, st);
+    prof_end(pc, PVB_STAGE_FINISH, st);
     return PVB_OK;
 }
 
@@ -274,16 +291,6 @@ PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream
 }
 
 // ---- host-buffer pipeline ---------------------------------------------------------------
-static size_t mask_elt_bytes(int dt)
-{
-    switch (dt) {
-    case PVB_MASK_U8: case PVB_MASK_I8: return 1;
-    case PVB_MASK_I16: return 2;
-    case PVB_MASK_I32: case PVB_MASK_F32: return 4;
-    default: return 8;
-    }
-}
-
 struct HostSlot { size_t mask, vertex, out, ws, end; };
 
 static int host_slot_layout(const pvb_desc *d, int chunk, HostSlot *S, pvb_desc *dc)
@@ -438,8 +445,10 @@ PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant)
 
 PVB_API int pvb_profile_reset(void)
 {
-    for (auto &pc : g_prof_calls)
-        for (auto e : pc.ev) g_prof_pool.push_back(e);
+    for (auto &pc : g_prof_calls) {
+        for (auto e : pc.start) g_prof_pool.push_back(e);
+        for (auto e : pc.end) g_prof_pool.push_back(e);
+    }
     g_prof_calls.clear();
     return PVB_OK;
 }
@@ -449,15 +458,14 @@ PVB_API int pvb_profile_read(double *ms, int32_t n)
     if (!ms || n < PVB_STAGE_COUNT) return fail(PVB_ERR_INVALID, "ms must hold PVB_STAGE_COUNT doubles");
     int calls = 0;
     for (auto &pc : g_prof_calls) {
-        cudaError_t e = cudaEventSynchronize(pc.ev[PVB_STAGE_COUNT]);
-        if (e != cudaSuccess) { cuda_fail(e, "profile event sync"); return -1; }
         for (int i = 0; i < PVB_STAGE_COUNT; ++i) {
+            cudaError_t e = cudaEventSynchronize(pc.end[i]);
             float t = 0.f;
-            e = cudaEventElapsedTime(&t, pc.ev[i], pc.ev[i + 1]);
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&t, pc.start[i], pc.end[i]);
             if (e != cudaSuccess) { cuda_fail(e, "profile elapsed"); return -1; }
             ms[i] += (double)t;
         }
-        ++calls;
+        if (pc.head) ++calls;
     }
     pvb_profile_reset();
     return calls;

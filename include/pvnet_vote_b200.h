@@ -177,10 +177,9 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_FINISH = 3,   /* winner + refit, or covariance */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
-/* Launch-shape tuning of the vote kernel (tooling; process-wide).  vote_chunk: pixels per CTA (multiple
- * of 256, <=0 keeps the current value; currently ignored); vote_variant: pixel-tile size per CTA,
- * 0 = 512 (default), 1 = 256, 2 = 1024.  Results do not depend on either. */
-PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant);
+/* Tuning switch (tooling; process-wide).  reserved: pass 0.  vote_variant: pixel-tile size per vote CTA,
+ * 0 = 512 (default), 1 = 256, 2 = 1024.  Results do not depend on it. */
+PVB_API int pvb_set_tuning(int32_t reserved, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);
 PVB_API int pvb_profile_read(double *ms, int32_t n);
 

@@ -129,6 +129,53 @@ def test_distribution_matches_reference_under_same_seed(pvb, ref):
     assert torch.allclose(got, want, rtol=2e-3, atol=1e-3), (got - want).abs().max().item()
 
 
+def test_distribution_with_thinning_matches_reference(pvb, ref):
+    """fg > max_num: the reference thins, recomputes `foreground` (:219-223) and divides counts by it."""
+    _, gpu = ref
+    mask, vertex, _ = _inputs("small", seed=201)
+    mean = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, seed=1)
+    torch.manual_seed(10)
+    _, want = gpu.estimate_voting_distribution_with_mean(mask, vertex, mean.clone(), round_hyp_num=64, min_hyp_num=256,
+                                                         max_num=700)
+    torch.manual_seed(10)
+    _, got = pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=64, min_hyp_num=256,
+                                                        max_num=700, rng="torch")
+    assert torch.allclose(got, want, rtol=2e-3, atol=1e-3), (got - want).abs().max().item()
+
+
+def test_v1_layer_matches_reference(pvb, ref):
+    """ransac_voting_layer (v1, torch.inverse instead of b_inv) -- imported by resnet18.py:5."""
+    _, gpu = ref
+    mask, vertex, _ = _inputs("small", seed=202)
+    torch.manual_seed(4)
+    want = gpu.ransac_voting_layer(mask, vertex, 64, inlier_thresh=0.99)
+    torch.manual_seed(4)
+    got = pvb.ransac_voting_layer(mask, vertex, 64, inlier_thresh=0.99, rng="torch")
+    assert (got - want).norm(dim=-1).max().item() < 1e-3
+
+
+def test_production_call_pattern(pvb, ref):
+    """decode_keypoint's two call patterns (resnet18.py:70-76) on the strided NCHW view with an argmax mask."""
+    _, gpu = ref
+    from clean_pvnet_b200 import synth
+    mask, vertex, _ = synth.make_inputs("small", device="cuda", seed=203, layout="planar")
+    seg = torch.stack([1.0 - mask.float(), mask.float()], dim=1)           # [B,2,H,W] logits
+    amask = torch.argmax(seg, 1)                                           # int64, as resnet18.py:69
+    torch.manual_seed(6)
+    want = gpu.ransac_voting_layer_v3(amask, vertex, 128, inlier_thresh=0.99, max_num=100)
+    torch.manual_seed(6)
+    got = pvb.ransac_voting_layer_v3(amask, vertex, 128, inlier_thresh=0.99, max_num=100, rng="torch")
+    assert (got - want).norm(dim=-1).max().item() < 1e-3
+    torch.manual_seed(7)
+    mean_w = gpu.ransac_voting_layer_v3(amask, vertex, 512, inlier_thresh=0.99)
+    _, var_w = gpu.estimate_voting_distribution_with_mean(amask, vertex, mean_w)
+    torch.manual_seed(7)
+    mean_g = pvb.ransac_voting_layer_v3(amask, vertex, 512, inlier_thresh=0.99, rng="torch")
+    _, var_g = pvb.estimate_voting_distribution_with_mean(amask, vertex, mean_g, rng="torch")
+    assert (mean_g - mean_w).norm(dim=-1).max().item() < 1e-3
+    assert torch.allclose(var_g, var_w, rtol=5e-3, atol=2e-3), (var_g - var_w).abs().max().item()
+
+
 def test_philox_mode_is_statistically_equivalent(pvb, ref):
     """Default (philox) sampling is a different random stream, not a different estimator."""
     _, gpu = ref

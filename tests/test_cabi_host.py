@@ -148,3 +148,17 @@ def test_missing_library_fails_loudly(pvb, monkeypatch):
     monkeypatch.setattr(pvb._lib, "LIB_PATH", "/nonexistent/libpvnet_vote_b200.so")
     with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
         pvb._lib.load()
+
+
+def test_plain_c_consumer_links_and_runs(pvb, tmp_path):
+    """include/pvnet_vote_b200.h is C99 and the shared library needs nothing but libc/libstdc++ at link time."""
+    import subprocess
+    exe = str(tmp_path / "cabi_smoke")
+    libdir = os.path.dirname(pvb._lib.LIB_PATH)
+    cc = os.environ.get("CC", "gcc")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cabi_smoke.c"), "-L", libdir, "-lpvnet_vote_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout
+    assert "sizeof(pvb_desc)=128" in r.stdout

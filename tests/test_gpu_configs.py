@@ -90,3 +90,19 @@ def test_large_batch_many_images(pvb):
     parts = [pvb.ransac_voting_layer_v3(mask[i:i + 16], vertex[i:i + 16], 512, inlier_thresh=0.99, seed=61, img_base=i)
              for i in range(0, 64, 16)]
     assert torch.equal(full, torch.cat(parts))
+
+
+def test_cfg5_maximum_batch(pvb):
+    """Stress sweep batch size: B=256 at 640x640 in ONE launch set (K=4, hn=128 keep the dense input at 3.4 GB);
+    fill varies 1-80 % per image; image 200 equals its stand-alone result."""
+    cfg = dict(B=256, H=640, W=640, K=4, hn=128, fill=(0.01, 0.80), kind="blob")
+    from clean_pvnet_b200 import synth
+    mask, vertex, _ = synth.make_inputs(cfg, device="cuda", seed=1242)
+    out, dbg = pvb.ransac_voting_layer_v3(mask, vertex, 128, inlier_thresh=0.99, seed=71, debug=True)
+    assert out.shape == (256, 4, 2) and torch.isfinite(out).all()
+    tn, nz, fg = dbg["tn"].cpu(), dbg["nz"].cpu(), dbg["fgsum"].cpu()
+    assert (tn[fg <= 30000] == nz[fg <= 30000]).all()
+    assert ((tn[fg > 30000] - 30000).abs() < 6 * 30000 ** 0.5).all()
+    assert int((fg > 30000).sum()) > 50 and int((fg <= 30000).sum()) > 5
+    solo = pvb.ransac_voting_layer_v3(mask[200:201], vertex[200:201], 128, inlier_thresh=0.99, seed=71, img_base=200)
+    assert torch.equal(solo[0], out[200])

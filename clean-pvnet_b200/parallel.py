@@ -17,20 +17,39 @@ def shard_bounds(total, world_size, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def all_gather_ragged(local, total, group=None):
-    """all_gather of per-rank slices [n_r, ...] (n_r from shard_bounds) into [total, ...]."""
+def all_gather_ragged(local, total, group=None, async_op=False):
+    """all_gather of per-rank slices [n_r, ...] (n_r from shard_bounds) into [total, ...].
+
+    async_op=True returns (finish, work): the collective is enqueued on NCCL's own stream (after the producer of
+    `local` on the current stream) so it overlaps whatever the caller launches next; call `work.wait()` and then
+    `finish()` to get the gathered tensor."""
     world = dist.get_world_size(group)
     if world == 1:
-        return local
+        return (lambda: local, None) if async_op else local
     sizes = [shard_bounds(total, world, r) for r in range(world)]
     nmax = max(hi - lo for lo, hi in sizes)
-    pad = local.new_zeros((nmax,) + tuple(local.shape[1:]))
-    pad[: local.shape[0]] = local
+    even = all(hi - lo == nmax for lo, hi in sizes)
+    if even:
+        pad = local.contiguous()
+    else:
+        pad = local.new_zeros((nmax,) + tuple(local.shape[1:]))
+        pad[: local.shape[0]] = local
     out = local.new_empty((world * nmax,) + tuple(local.shape[1:]))
-    dist.all_gather_into_tensor(out, pad, group=group) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda \
-        else dist.all_gather(list(out.view(world, nmax, *local.shape[1:]).unbind(0)), pad, group=group)
-    out = out.view(world, nmax, *local.shape[1:])
-    return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    if hasattr(dist, "all_gather_into_tensor") and local.is_cuda:
+        work = dist.all_gather_into_tensor(out, pad, group=group, async_op=async_op)
+    else:
+        work = dist.all_gather(list(out.view(world, nmax, *local.shape[1:]).unbind(0)), pad, group=group,
+                               async_op=async_op)
+
+    def finish():
+        if even:
+            return out
+        o = out.view(world, nmax, *local.shape[1:])
+        return torch.cat([o[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+    if async_op:
+        return finish, work
+    return finish()
 
 
 def sharded_ransac_voting_layer_v3(mask_local, vertex_local, round_hyp_num, total_images, inlier_thresh=0.999,

@@ -6,17 +6,20 @@
 // Here: one launch each for the whole batch, no [hn,vn,tn] byte tensor, no host sync.
 //
 // vote_kernel design (FP32-issue bound, not HBM bound: hn tests per 16 loaded bytes):
-//   * a CTA owns one (image b, keypoint k, hypothesis slice, pixel chunk);
-//   * every thread keeps HPT hypotheses and their counters in registers;
-//   * pixels are staged through shared memory as 6-float "cone records" and broadcast to all
-//     threads (LDS.128 + LDS.64 per pixel per warp);
+//   * a CTA owns one (image b, keypoint k, hypothesis slice, tile of 512 selected pixels);
+//   * every thread keeps HPT hypotheses and their tallies in registers;
+//   * the tile is staged once through shared memory as 6-float "cone records", relative to a
+//     tile-local origin (centre of the tile's bounding box), and broadcast to all threads
+//     (3 LDS.128 per 2 pixels per warp);
 //   * the inlier test  cos(angle(v, h-c)) > t  is evaluated in the rotated frame of the pixel's
-//     unit vector u:   a = u.(h-c),  p = u_perp.(h-c),   inlier <=> kappa*a - |p| > 0,
+//     unit vector u:   a = u.(h-c),  p = u_perp.(h-c),   inlier <=> m = kappa*a - |p| > 0,
 //     kappa = tan(acos t).  With the record (A1,A2,A3,B1,B2,B3) this is 4 FFMA + 1 FADD per test;
-//   * that test is algebraically, not bitwise, the reference predicate.  A guard band delta
-//     (DESIGN.md "Guard band") bounds every rounding difference between the two; whenever
-//     |kappa*a-|p|| < delta the pixel is re-evaluated with the reference's exact operation
-//     sequence (vote_exact).  Counts are therefore identical to the reference's.
+//     the tally is the sign bit of m (LEA.HI), the smallest |m| per 16-pixel block and hypothesis
+//     is tracked with FMNMX3: 454 SASS instructions per 64 tests per thread;
+//   * m is algebraically, not bitwise, the reference predicate.  A guard band delta = band * S
+//     (tools/band_check.c) bounds every rounding difference between the two; blocks
+//     whose smallest |m| falls inside it are re-evaluated -- warp-cooperatively -- with the
+//     reference's exact operation sequence (vote_exact).  Counts equal the reference's.
 #include <math_constants.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -305,7 +308,7 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
 
 // ---------------------------------------------------------------------------------
 // winner (torch.max semantics: first maximal index, ransac_voting_gpu.py:160-167) + least-squares
-// refit over the winner's inliers (:177-196).  One CTA per (image, keypoint).
+// refit over the winner's inliers (:177-196).  RF_CHUNK pixels per CTA, ticketed deterministic reduction.
 // ---------------------------------------------------------------------------------
 constexpr int RF_THREADS = 128;
 constexpr int RF_CHUNK = 2048;     // pixels per CTA

@@ -93,12 +93,17 @@ __device__ __forceinline__ float cone_margin(const float4 ra, const float2 rb, f
     return ap - fabsf(pp);
 }
 
-template <int HPT, int NT, int MINB, int VOTE_TILE>
+// WS = warps that together hold one hypothesis slice (HPT*WS*32 hypotheses).  With fewer than 512 hypotheses per
+// keypoint the remaining NT/32/WS warp teams of the CTA split the tile's 16-pixel blocks between them, so every
+// thread still owns HPT hypotheses and the inner loop keeps its instruction mix.
+template <int HPT, int NT, int MINB, int VOTE_TILE, int WS>
 __global__ void __launch_bounds__(NT, MINB)
 vote_kernel(const VoteK p)
 {
     constexpr int PPT = VOTE_TILE / NT;               // pixels staged per thread
     constexpr int NW = NT / 32;
+    constexpr int TEAM = WS * 32;                     // threads per hypothesis slice
+    constexpr int TEAMS = NT / TEAM;                  // teams sharing the staged tile
     __shared__ __align__(16) float4 s_a[VOTE_TILE];   // (A1, A2, A3, B1)
     __shared__ __align__(16) float2 s_b[VOTE_TILE];   // (B2, B3)
     __shared__ float s_box[4][NW];
@@ -115,7 +120,8 @@ vote_kernel(const VoteK p)
     const float2 *hyp = a.hyp + ((size_t)b * a.K + k) * a.hn;
     const float2 *xy = a.xy + (size_t)b * a.cap + t0;
     const float2 *dk = a.dirs + ((size_t)b * a.K + k) * a.cap + t0;
-    const int hbase = slice * (NT * HPT) + tid;
+    const int team = tid / TEAM;
+    const int hbase = slice * (TEAM * HPT) + (tid - team * TEAM);
 
     // ---- stage 1: load this tile's pixels, bounding box -> tile-local origin for the fast path.
     // The guard band scales with S = |h-o|_1 + max|c-o|_1, so a local origin keeps it tight.
@@ -178,7 +184,7 @@ vote_kernel(const VoteK p)
     int neg[HPT];   // tests whose margin is negative (sign bit) = non-inliers, padding included
 #pragma unroll
     for (int j = 0; j < HPT; ++j) {
-        const int h = hbase + j * NT;
+        const int h = hbase + j * TEAM;
         const float2 q = (h < a.hn) ? hyp[h] : make_float2(0.f, 0.f);
         float xc = q.x - ox, yc = q.y - oy;
         const float S = fabsf(xc) + fabsf(yc) + cmax;
@@ -191,7 +197,9 @@ vote_kernel(const VoteK p)
 
     const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(s_a);
     const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(s_b);
-    for (int i0 = 0; i0 < npad; i0 += VOTE_BLOCK) {
+    int mine = 0;   // pixels (padding included) this team has scored
+    for (int i0 = team * VOTE_BLOCK; i0 < npad; i0 += TEAMS * VOTE_BLOCK) {
+        mine += VOTE_BLOCK;
         const uint32_t sa = sa0 + (uint32_t)i0 * 16u, sb = sb0 + (uint32_t)i0 * 8u;
         float mn[HPT];   // smallest |margin| of each hypothesis over this block
 #pragma unroll
@@ -231,7 +239,7 @@ vote_kernel(const VoteK p)
                     bm &= bm - 1;
                     const float hx_ = __shfl_sync(0xffffffffu, hxc[j], L), hy_ = __shfl_sync(0xffffffffu, hyc[j], L);
                     const float dl_ = __shfl_sync(0xffffffffu, dl[j], L);
-                    const int h = hbase - lane + L + j * NT;
+                    const int h = hbase - lane + L + j * TEAM;
                     const float2 q = (h < a.hn) ? __ldg(hyp + h) : make_float2(0.f, 0.f);
                     int delta = 0;
                     if (lane < nb) {
@@ -250,8 +258,8 @@ vote_kernel(const VoteK p)
     int *counts = a.counts + ((size_t)b * a.K + k) * a.hn;
 #pragma unroll
     for (int j = 0; j < HPT; ++j) {
-        const int h = hbase + j * NT;
-        const int cnt = npad - neg[j];
+        const int h = hbase + j * TEAM;
+        const int cnt = mine - neg[j];
         if (h < a.hn && cnt) atomicAdd(counts + h, cnt);
     }
 }
@@ -291,17 +299,19 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
     VoteK p;
     p.a = a;
     p.cone = make_cone(a.thresh);
-#define PVB_VOTE(HPT, NT, MINB, TILE)                                                   \
+#define PVB_VOTE(HPT, NT, MINB, TILE, WS)                                               \
     do {                                                                                \
-        const int slices = (a.hn + (HPT) * (NT) - 1) / ((HPT) * (NT));                  \
+        const int slices = (a.hn + (HPT) * (WS) * 32 - 1) / ((HPT) * (WS) * 32);        \
         dim3 g((a.cap + (TILE) - 1) / (TILE), a.K * slices, a.B);                       \
-        vote_kernel<HPT, NT, MINB, TILE><<<g, NT, 0, st>>>(p);                          \
+        vote_kernel<HPT, NT, MINB, TILE, WS><<<g, NT, 0, st>>>(p);                      \
     } while (0)
-    if (a.hn <= 128) PVB_VOTE(1, 128, 1, 256);
-    else if (a.hn <= 256) PVB_VOTE(2, 128, 1, 256);
-    else if (g_vote_variant == 1) PVB_VOTE(4, 128, 8, 256);
-    else if (g_vote_variant == 2) PVB_VOTE(4, 128, 8, 1024);
-    else PVB_VOTE(4, 128, 8, 512);     // measured best on B200 (profiles/r01_vote_tuning.md)
+    if (a.hn <= 32) PVB_VOTE(1, 128, 8, 512, 1);
+    else if (a.hn <= 64) PVB_VOTE(2, 128, 8, 512, 1);
+    else if (a.hn <= 128) PVB_VOTE(4, 128, 8, 512, 1);
+    else if (a.hn <= 256) PVB_VOTE(4, 128, 8, 512, 2);
+    else if (g_vote_variant == 1) PVB_VOTE(4, 128, 8, 256, 4);
+    else if (g_vote_variant == 2) PVB_VOTE(4, 128, 8, 1024, 4);
+    else PVB_VOTE(4, 128, 8, 512, 4);     // measured best on B200 (profiles/r01_vote_tuning.md)
 #undef PVB_VOTE
     return cudaGetLastError();
 }

@@ -325,8 +325,24 @@ constexpr int RF_CHUNK = 2048;     // pixels per CTA
 
 int refit_splits_for(int cap) { return (cap + RF_CHUNK - 1) / RF_CHUNK; }
 
+// The reference predicate for ONE hypothesis (the winner) against many pixels: same cone test and guard band as the
+// vote kernel, with the pixel itself as origin (d = RN(h-c) is the reference's own rounded difference) and without
+// normalising v:  m' = kappa*(v.d) - |v x d| = |v|*m,  flagged when m'^2 < (band*|d|_1)^2*|v|^2 (or anything unusual),
+// in which case the exact operation sequence decides.
+__device__ __forceinline__ bool vote_winner(float vx, float vy, float cx, float cy, float hx, float hy,
+                                            const ConeParams &cone)
+{
+    const float dx = __fsub_rn(hx, cx), dy = __fsub_rn(hy, cy);
+    const float n1sq = fmaf(vx, vx, vy * vy);
+    const float S = fabsf(dx) + fabsf(dy);
+    const float m = cone.kappa * fmaf(vx, dx, vy * dy) - fabsf(fmaf(vx, dy, -(vy * dx)));
+    const float thr = cone.band * S;
+    const bool safe = (n1sq > 1e-10f) && (n1sq < 1e8f) && (S <= 1e6f) && (m * m > thr * thr * n1sq * 1.0001f);
+    return safe ? (m > 0.f) : vote_exact(vx, vy, cx, cy, hx, hy, cone.thresh);
+}
+
 __global__ void __launch_bounds__(RF_THREADS)
-refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__restrict__ out)
+refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__restrict__ out, ConeParams cone)
 {
     const int split = blockIdx.x, k = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -367,13 +383,23 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__res
     const float2 *dk = a.dirs + bk * a.cap;
     const int t_end = min(tn, (split + 1) * RF_CHUNK);
     double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
-    for (int t = split * RF_CHUNK + tid; t < t_end; t += RF_THREADS) {
-        const float2 v = __ldg(dk + t), c = __ldg(xy + t);
-        if (vote_exact(v.x, v.y, c.x, c.y, wpt.x, wpt.y, a.thresh)) {
-            const double nx = (double)v.y, ny = -(double)v.x;       // normal = (d_y, -d_x)  (:178-180)
-            const double bb = nx * (double)c.x + ny * (double)c.y;   // b = n . c             (:189)
-            a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;          // ATA                   (:190)
-            b0 += nx * bb; b1 += ny * bb;                            // ATb                   (:191)
+    constexpr int RU = 4;     // loads in flight per thread (the loop is latency bound: 16 pixels per thread)
+    for (int t0 = split * RF_CHUNK + tid; t0 < t_end; t0 += RF_THREADS * RU) {
+        float2 v[RU], c[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int t = t0 + u * RF_THREADS;
+            v[u] = make_float2(0.f, 0.f); c[u] = make_float2(0.f, 0.f);
+            if (t < t_end) { v[u] = __ldg(dk + t); c[u] = __ldg(xy + t); }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (t0 + u * RF_THREADS < t_end && vote_winner(v[u].x, v[u].y, c[u].x, c[u].y, wpt.x, wpt.y, cone)) {
+                const double nx = (double)v[u].y, ny = -(double)v[u].x;       // normal = (d_y, -d_x)  (:178-180)
+                const double bb = nx * (double)c[u].x + ny * (double)c[u].y;   // b = n . c             (:189)
+                a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;                // ATA                   (:190)
+                b0 += nx * bb; b1 += ny * bb;                                  // ATb                   (:191)
+            }
         }
     }
     a00 = warp_sum(a00); a01 = warp_sum(a01); a11 = warp_sum(a11); b0 = warp_sum(b0); b1 = warp_sum(b1);
@@ -405,7 +431,7 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__res
 cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, cudaStream_t st)
 {
     dim3 g(rs.splits, a.K, a.B);
-    refit_kernel<<<g, RF_THREADS, 0, st>>>(a, win, rs, out_kpt);
+    refit_kernel<<<g, RF_THREADS, 0, st>>>(a, win, rs, out_kpt, make_cone(a.thresh));
     return cudaGetLastError();
 }
 

@@ -42,7 +42,7 @@ int main(int argc, char **argv)
     const float kappa = (float)(sq / t);
     const double G = 1.0 / (t * sq), u = ldexp(1.0, -24), theta = acos(t);
     double rmax = 0, rmax_d = 0;
-    long mism = 0, near = 0;
+    long mism = 0, near = 0, w_total = 0, w_safe = 0;
     for (long it = 0; it < n; ++it) {
         /* pixel, direction (norm around 1 with jitter, like a network output) */
         float cx = (float)(int)(uni() * W), cy = (float)(int)(uni() * H);
@@ -72,6 +72,21 @@ int main(int argc, char **argv)
         float a1 = kappa * ux, a2 = kappa * uy;
         float A3 = -fmaf(a1, cxc, a2 * cyc);
         float B1 = -uy, B2 = ux, B3 = fmaf(uy, cxc, -(ux * cyc));
+        /* refit prefilter (vote_winner in vote.cu): pixel-origin, unnormalised */
+        {
+            float ddx = hx - cx, ddy = hy - cy;
+            float n1sq = fmaf(vx, vx, vy * vy);
+            float Sd = fabsf(ddx) + fabsf(ddy);
+            float mw = kappa * fmaf(vx, ddx, vy * ddy) - fabsf(fmaf(vx, ddy, -(vy * ddx)));
+            float bandf = (float)(1.25 * u * (18.0 + 22.0 * kappa + 9.0 * G));
+            float thr = bandf * Sd;
+            int safe = (n1sq > 1e-10f) && (n1sq < 1e8f) && (Sd <= 1e6f) && (mw * mw > thr * thr * n1sq * 1.0001f);
+            ++w_total;
+            if (safe) {
+                ++w_safe;
+                if ((mw > 0.f) != vote_one(vx, vy, cx, cy, hx, hy, thresh)) { printf("WINNER PREFILTER MISMATCH m=%g S=%g\n", mw, Sd); return 1; }
+            }
+        }
         float hxc = hx - ox, hyc = hy - oy;
         float ap = fmaf(a1, hxc, fmaf(a2, hyc, A3));
         float pp = fmaf(B1, hxc, fmaf(B2, hyc, B3));
@@ -94,6 +109,7 @@ int main(int argc, char **argv)
     printf("thresh=%.6f kappa=%.6f G=%.3f  samples=%ld  mismatches=%ld  in-band=%ld\n", thresh, kappa, G, n, mism, near);
     printf("max |m|/(u*S) over mismatches = %.3f   (kernel band constant 1.25*(18+22k+9G) = %.1f)\n",
            rmax, 1.25 * (18 + 22 * kappa + 9 * G));
+    printf("refit prefilter: %ld of %ld boundary samples decided without the exact path, 0 disagreements\n", w_safe, w_total);
     printf("max |m| / analytic bound [2*err_fast(S) + 9uG|d|] = %.3f (must be < 1)\n", rmax_d);
     return 0;
 }

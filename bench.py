@@ -282,6 +282,14 @@ def run_ours(args):
             lambda: pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, seed=7, img_base=rank * B), 10)
         extras["v3_latency_b1_ms"] = timed(
             lambda: pvb.ransac_voting_layer_v3(mask[:1], vertex[:1], HN, inlier_thresh=THRESH, seed=7), 50)
+        # decode_keypoint's argmax fused into the select kernel (pvb_decode_v3) vs torch.argmax + v3
+        from clean_pvnet_b200 import decode as _dec
+        seg = torch.stack([1.0 - mask.float(), mask.float()], dim=1).contiguous()
+        extras["decode_front_fused_ms"] = timed(
+            lambda: _dec._decode_v3(seg, vertex, HN, THRESH, 5, 30000, 7, rank * B), 30)
+        extras["decode_front_unfused_ms"] = timed(
+            lambda: pvb.ransac_voting_layer_v3(torch.argmax(seg, 1), vertex, HN, inlier_thresh=THRESH, seed=7,
+                                               img_base=rank * B), 30)
     except Exception as e:
         extras["error"] = str(e)
 

@@ -150,6 +150,7 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     s.min_num = d->min_num; s.max_num = d->max_num; s.img_base = d->img_base;
     s.seed = d->seed; s.tag_sel = d->rng_tag_sel ? (uint32_t)d->rng_tag_sel : tag_sel;
     s.rowwise_gather = 0;
+    s.seg_classes = 0; s.seg_cs = 0; s.mask_out = nullptr;
     s.bits = reinterpret_cast<uint32_t *>(w + L.bits);
     s.wordoff = reinterpret_cast<int *>(w + L.wordoff);
     s.blocktot = reinterpret_cast<int *>(w + L.blocktot);
@@ -242,6 +243,30 @@ PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const floa
     if (rc) return rc;
     if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
     if (d->B == 0) return PVB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ProfCall *pc = prof_begin(true);
+    rc = run_front(P, st, pc);
+    if (rc) return rc;
+    prof_start(pc, PVB_STAGE_FINISH, st);
+    cudaError_t e = launch_refit(P.v, P.win, P.refit, out_kpt, st);
+    if (e != cudaSuccess) return cuda_fail(e, "refit kernel");
+    prof_end(pc, PVB_STAGE_FINISH, st);
+    return PVB_OK;
+}
+
+PVB_API int pvb_decode_v3(const pvb_desc *d, const float *seg, int32_t classes, int64_t class_stride, int64_t *mask_out,
+                          const float *vertex, const int32_t *idxs, const float *selection, float *out_kpt,
+                          void *workspace, size_t workspace_bytes, pvb_stream_t stream)
+{
+    if (classes < 1 || classes > 4096) return fail(PVB_ERR_INVALID, "classes must be in [1,4096]");
+    Plan P;
+    int rc = make_plan(d, seg, vertex, idxs, selection, workspace, workspace_bytes, 1u, 2u, &P);
+    if (rc) return rc;
+    if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
+    if (d->B == 0) return PVB_OK;
+    P.s.seg_classes = classes;
+    P.s.seg_cs = class_stride;
+    P.s.mask_out = reinterpret_cast<long long *>(mask_out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ProfCall *pc = prof_begin(true);
     rc = run_front(P, st, pc);

@@ -15,6 +15,9 @@ struct SelectArgs {
     const float *selection;       // optional [B,H,W]
     int B, H, W, K, nwords, nblocks, cap, min_num, max_num, img_base;
     int rowwise_gather;           // 1: vertex is zero-copy host memory, read whole pixel rows per warp
+    int seg_classes;              // > 0: `mask` points to fp32 logits [B,C,H,W]; the mask is argmax over C
+    long long seg_cs;             // class stride of the logits (elements)
+    long long *mask_out;          // optional int64 [B,H,W] argmax output
     uint64_t seed;
     uint32_t tag_sel;
     uint32_t *bits;

@@ -89,6 +89,68 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
     }
 }
 
+// Fused front end of decode_keypoint (lib/networks/pvnet/resnet18.py:69): the mask is torch.argmax(seg, 1) -- first
+// maximal class, NaN counts as maximal like torch -- computed on the fly from the fp32 logits [B,C,H,W]; optionally
+// also written out as the int64 mask decode_keypoint returns.  Otherwise identical to mask_bits_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(MB_WARPS * 32)
+seg_bits_kernel(const float *__restrict__ seg, long long sb, long long sc, long long sy, long long sx, int C, int H, int W,
+                int nwords, long long *__restrict__ mask_out, uint32_t *__restrict__ bits,
+                unsigned long long *__restrict__ fgsum, int *__restrict__ nz)
+{
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w0 = (blockIdx.x * MB_WARPS + warp) * MB_WORDS;
+    if (w0 >= nwords) return;
+    const int HW = H * W;
+    const float *sbp = seg + (long long)b * sb;
+    const bool contig = (sx == 1 && sy == W);
+    uint32_t myword = 0, sum = 0;
+    for (int i0 = 0; i0 < MB_WORDS; i0 += MB_UNROLL) {
+        long long off[MB_UNROLL];
+        float best[MB_UNROLL];
+        int idx[MB_UNROLL];
+        bool inb[MB_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MB_UNROLL; ++u) {           // MB_UNROLL class-0 loads in flight per lane
+            const int p = (w0 + i0 + u) * 32 + lane;
+            inb[u] = p < HW;
+            off[u] = p;
+            if (!contig && inb[u]) { const int y = p / W; off[u] = (long long)y * sy + (long long)(p - y * W) * sx; }
+            best[u] = inb[u] ? __ldg(sbp + off[u]) : 0.f;
+            idx[u] = 0;
+        }
+        for (int c = 1; c < C; ++c) {
+            float v[MB_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MB_UNROLL; ++u) v[u] = inb[u] ? __ldg(sbp + off[u] + (long long)c * sc) : 0.f;
+#pragma unroll
+            for (int u = 0; u < MB_UNROLL; ++u)
+                if (v[u] > best[u] || (v[u] != v[u] && best[u] == best[u])) { best[u] = v[u]; idx[u] = c; }
+        }
+#pragma unroll
+        for (int u = 0; u < MB_UNROLL; ++u) {
+            const int p = (w0 + i0 + u) * 32 + lane;
+            if (mask_out && inb[u]) mask_out[(size_t)b * HW + p] = idx[u];
+            bool sel;
+            uint32_t val;
+            if (MODE == PVB_SELECT_BYTE) { val = (uint32_t)(uint8_t)idx[u]; sel = val != 0; }
+            else { sel = (idx[u] == 1); val = sel; }
+            if (!inb[u]) { sel = false; val = 0; }
+            const uint32_t word = __ballot_sync(0xffffffffu, sel);
+            if (lane == i0 + u) myword = word;
+            sum += val;
+        }
+    }
+    if (lane < MB_WORDS && w0 + lane < nwords) bits[(size_t)b * nwords + w0 + lane] = myword;
+    const int s = warp_sum((int)sum);
+    const int c = warp_sum(__popc(myword));
+    if (lane == 0) {
+        atomicAdd(fgsum + b, (unsigned long long)(unsigned)s);
+        atomicAdd(nz + b, c);
+    }
+}
+
 // One CTA per 128 bitmap words: decides skip / thinning for its image (ransac_voting_gpu.py:129-138),
 // applies the Bernoulli thinning to its words, and writes the exclusive popcount prefix WITHIN the
 // block plus the block total; the gather kernel adds the totals of the preceding blocks.
@@ -277,6 +339,14 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
         else PVB_MB2(T, PVB_SELECT_EQ1);                                                                 \
     } while (0)
     const bool contig = (a.msx == 1 && a.msy == a.W);
+    if (a.seg_classes > 0) {
+        if (a.select_mode == PVB_SELECT_BYTE)
+            seg_bits_kernel<PVB_SELECT_BYTE><<<g1, MB_WARPS * 32, 0, st>>>((const float *)a.mask, a.msb, a.seg_cs, a.msy, a.msx,
+                                                                          a.seg_classes, a.H, a.W, nwords, a.mask_out, a.bits, a.fgsum, a.nz);
+        else
+            seg_bits_kernel<PVB_SELECT_EQ1><<<g1, MB_WARPS * 32, 0, st>>>((const float *)a.mask, a.msb, a.seg_cs, a.msy, a.msx,
+                                                                         a.seg_classes, a.H, a.W, nwords, a.mask_out, a.bits, a.fgsum, a.nz);
+    } else
     switch (a.mask_dtype) {
     case PVB_MASK_U8: PVB_MB(uint8_t); break;
     case PVB_MASK_I8: PVB_MB(int8_t); break;

@@ -137,6 +137,16 @@ PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const floa
                          const int32_t *idxs, const float *selection, float *out_kpt,
                          void *workspace, size_t workspace_bytes, pvb_stream_t stream);
 
+/* Fused front end of Resnet18.decode_keypoint (lib/networks/pvnet/resnet18.py:65-76): same as
+ * pvb_ransac_voting_v3, but the mask is torch.argmax(seg, 1) (:69) computed on the fly from the fp32 logits
+ *   seg  device fp32 [B,classes,H,W]; d->mask_stride = its (B,H,W) strides, class_stride its class stride (elements);
+ *        d->mask_dtype is ignored.  First maximal class wins, NaN counts as maximal (torch.argmax semantics).
+ *   mask_out optional device int64 [B,H,W] contiguous: receives the argmax mask decode_keypoint returns (:73,:76).
+ * d->select_mode applies to the class index exactly as it would to the mask tensor. */
+PVB_API int pvb_decode_v3(const pvb_desc *d, const float *seg, int32_t classes, int64_t class_stride, int64_t *mask_out,
+                          const float *vertex, const int32_t *idxs, const float *selection, float *out_kpt,
+                          void *workspace, size_t workspace_bytes, pvb_stream_t stream);
+
 /* estimate_voting_distribution_with_mean (ransac_voting_gpu.py:202-274).
  *   mean device fp32 [B,K,2];  out_cov device fp32 [B,K,2,2].  d->select_mode must be
  *   PVB_SELECT_EQ1 to match the reference (:207).  idxs optional int32 [B,hn,K,2] (the 16

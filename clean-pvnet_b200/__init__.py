@@ -11,7 +11,7 @@ from . import _lib  # noqa: F401
 from . import ransac_voting  # noqa: F401
 from . import ransac_voting_gpu  # noqa: F401
 from . import decode  # noqa: F401
-from .decode import decode_keypoint  # noqa: F401
+from .decode import decode_keypoint, uncertainty_pnp_weights  # noqa: F401
 from .ransac_voting_gpu import (  # noqa: F401
     estimate_voting_distribution_with_mean,
     ransac_voting_layer,
@@ -23,5 +23,5 @@ from .ransac_voting_gpu import (  # noqa: F401
 __all__ = [
     "ransac_voting_layer", "ransac_voting_layer_v3", "estimate_voting_distribution_with_mean",
     "ransac_voting_layer_v3_host", "install_as_reference_module", "ransac_voting", "ransac_voting_gpu",
-    "decode_keypoint",
+    "decode_keypoint", "uncertainty_pnp_weights",
 ]

@@ -298,6 +298,15 @@ PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask
     return PVB_OK;
 }
 
+PVB_API int pvb_uncertainty_weights(const float *cov, float *weights, int32_t n, pvb_stream_t stream)
+{
+    if (n < 0) return fail(PVB_ERR_INVALID, "n < 0");
+    if (n && (!cov || !weights)) return fail(PVB_ERR_INVALID, "NULL tensor");
+    if (reinterpret_cast<uintptr_t>(cov) & 15u) return fail(PVB_ERR_INVALID, "cov must be 16-byte aligned");
+    cudaError_t e = launch_pnp_weights(cov, weights, n, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "pnp weights kernel");
+}
+
 PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream)
 {
     pvb_layout L;

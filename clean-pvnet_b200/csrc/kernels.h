@@ -56,6 +56,9 @@ cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs,
 // ratio/threshold/weighted covariance -> out_cov [B][K][2][2]
 cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, cudaStream_t st);
 
+// inv(sqrtm(cov)) packed (wxx,wxy,wyy): cov [n][2][2] -> w [n][3]
+cudaError_t launch_pnp_weights(const float *cov, float *w, int n, cudaStream_t st);
+
 // twins of the reference extension on its own layouts
 cudaError_t launch_compat_generate(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
                                    int tn, int vn, int hn, bool vanishing, cudaStream_t st);

@@ -498,4 +498,38 @@ cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_c
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------
+// weights of the uncertainty PnP, inv(sqrtm(cov)) per keypoint packed as (wxx, wxy, wyy)
+// (lib/evaluators/linemod/pvnet.py:118-130: scipy.linalg.sqrtm + np.linalg.inv per keypoint on the CPU).
+// Closed form for a symmetric positive definite 2x2 M: sqrt(M) = (M + s I)/t, s = sqrt(det M), t = sqrt(tr M + 2 s),
+// so inv(sqrt(M)) = t * adj(M + s I) / det(M + s I).  cov[0,0] < 1e-6 or any NaN -> zeros, like the reference.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pnp_weights_kernel(const float *__restrict__ cov, float *__restrict__ w, int n)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = __ldg(reinterpret_cast<const float4 *>(cov) + i);
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    const bool bad = (c.x < 1e-6f) || (c.x != c.x) || (c.y != c.y) || (c.z != c.z) || (c.w != c.w);
+    if (!bad) {
+        const double a = c.x, b = 0.5 * ((double)c.y + (double)c.z), d = c.w;
+        const double det = a * d - b * b;
+        if (det > 0.0) {
+            const double s = sqrt(det), t = sqrt(a + d + 2.0 * s);
+            const double a2 = a + s, d2 = d + s;
+            const double den = a2 * d2 - b * b;
+            o0 = (float)(t * d2 / den); o1 = (float)(-t * b / den); o2 = (float)(t * a2 / den);
+        }
+    }
+    w[(size_t)i * 3] = o0; w[(size_t)i * 3 + 1] = o1; w[(size_t)i * 3 + 2] = o2;
+}
+
+cudaError_t launch_pnp_weights(const float *cov, float *w, int n, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    pnp_weights_kernel<<<(n + 127) / 128, 128, 0, st>>>(cov, w, n);
+    return cudaGetLastError();
+}
+
 } // namespace pvb

@@ -62,3 +62,21 @@ def _decode_v3(seg, vertex, hn, inlier_thresh, min_num, max_num, seed, img_base)
                                          None, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                          torch.cuda.current_stream(dev).cuda_stream))
     return mask, out
+
+
+def uncertainty_pnp_weights(var):
+    """inv(sqrtm(var)) per keypoint packed as (wxx, wxy, wyy) -- the `weights_2d` argument of
+    un_pnp_utils.uncertainty_pnp -- computed on the GPU in closed form instead of the per-keypoint
+    scipy.linalg.sqrtm / np.linalg.inv loop of lib/evaluators/linemod/pvnet.py:118-130.
+    var: CUDA float tensor [..., 2, 2] -> float32 [..., 3]."""
+    if not isinstance(var, torch.Tensor) or not var.is_cuda or var.shape[-2:] != (2, 2):
+        raise RuntimeError("var must be a CUDA tensor [...,2,2]")
+    lib = _lib.load()
+    v = var.float().contiguous()
+    out = torch.empty(tuple(v.shape[:-2]) + (3,), dtype=torch.float32, device=v.device)
+    n = v.numel() // 4
+    with torch.cuda.device(v.device):
+        if n:
+            _lib.check(lib.pvb_uncertainty_weights(v.data_ptr(), out.data_ptr(), n,
+                                                   torch.cuda.current_stream(v.device).cuda_stream))
+    return out

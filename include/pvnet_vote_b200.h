@@ -156,6 +156,12 @@ PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask
                                      float *out_cov, void *workspace, size_t workspace_bytes,
                                      pvb_stream_t stream);
 
+/* Weights of the uncertainty PnP (lib/evaluators/linemod/pvnet.py:118-130, a scipy.linalg.sqrtm + np.linalg.inv loop
+ * per keypoint on the CPU): weights[i] = (wxx, wxy, wyy) of inv(sqrtm(cov[i])), zeros where cov[i][0][0] < 1e-6, any
+ * entry is NaN or cov[i] is not positive definite.  cov device fp32 [n,2,2] (16-byte aligned), weights device fp32 [n,3].
+ * The result is what un_pnp_utils.uncertainty_pnp (lib/csrc/uncertainty_pnp/un_pnp_utils.py:6) takes as weights_2d. */
+PVB_API int pvb_uncertainty_weights(const float *cov, float *weights, int32_t n, pvb_stream_t stream);
+
 /* Reads the sticky status word of a workspace (synchronises `stream`). */
 PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream);
 

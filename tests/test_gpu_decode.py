@@ -57,3 +57,26 @@ def test_matches_reference_decode_flow(pvb):
     mean = pvb.ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99, seed=11)
     kpt, var = pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, seed=11)
     assert torch.equal(res["mask"], mask) and torch.equal(res["kpt_2d"], kpt) and torch.equal(res["var"], var)
+
+
+def test_uncertainty_pnp_weights_match_reference_formula(pvb):
+    """inv(sqrtm(cov)) weights vs the reference's own CPU code (evaluators/linemod/pvnet.py:118-130)."""
+    import numpy as np
+    import scipy.linalg
+    out = _network_output("small", 34)
+    res = pvb.decode_keypoint(dict(out), un_pnp=True, seed=13)
+    var = res["var"].clone()
+    var[0, 0] = 0.0                       # var[0,0] < 1e-6 -> zeros
+    var[1, 1, 0, 1] = float("nan")        # NaN -> zeros
+    got = pvb.uncertainty_pnp_weights(var).cpu().numpy()
+    v = var.cpu().numpy()
+    for b in range(v.shape[0]):
+        cov_invs = []
+        for vi in range(v.shape[1]):      # verbatim logic of the reference loop
+            if v[b, vi, 0, 0] < 1e-6 or np.sum(np.isnan(v[b])[vi]) > 0:
+                cov_invs.append(np.zeros([2, 2]).astype(np.float32))
+            else:
+                cov_invs.append(np.linalg.inv(scipy.linalg.sqrtm(v[b, vi])))
+        want = np.asarray(cov_invs).reshape([-1, 4])[:, (0, 1, 3)]
+        assert np.allclose(got[b], np.real(want), rtol=2e-4, atol=1e-6), (got[b], want)
+    assert (got[0, 0] == 0).all() and (got[1, 1] == 0).all()

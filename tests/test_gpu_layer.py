@@ -142,6 +142,26 @@ def test_v3_odd_image_sizes(pvb, oracle, H, W, K):
     _check_v3(pvb, oracle, mask, vertex, 40)
 
 
+@pytest.mark.parametrize("case", range(24))
+def test_v3_randomized_differential(pvb, oracle, case):
+    """Random shapes / keypoint counts / hypothesis counts / mask dtypes / layouts / thresholds / thinning against the oracle:
+    selected pixels, hypotheses (bit pattern), counts and winners exact, keypoints within 1e-4 px."""
+    rng = np.random.default_rng(1000 + case)
+    H, W = int(rng.integers(8, 160)), int(rng.integers(8, 200))
+    K, hn, B = int(rng.integers(1, 7)), int(rng.integers(1, 320)), int(rng.integers(1, 4))
+    fill = float(rng.uniform(0.05, 0.7))
+    cfg = dict(B=B, H=H, W=W, K=K, hn=hn, fill=(fill, fill), kind=str(rng.choice(["blob", "fragmented"])))
+    layout = str(rng.choice(["interleaved", "planar"]))
+    mask, vertex, _ = _inputs(pvb, cfg, seed=2000 + case, layout=layout, noise_deg=float(rng.uniform(0, 8)),
+                              outlier_frac=float(rng.uniform(0, 0.6)))
+    dtype = [torch.int64, torch.int32, torch.uint8, torch.bool, torch.float32][int(rng.integers(0, 5))]
+    fg = int(mask[0].sum())
+    max_num = int(rng.choice([30000, max(6, fg // 2), max(6, fg // 5)]))
+    thresh = float(rng.choice([0.99, 0.999, 0.95, 0.8]))
+    _check_v3(pvb, oracle, mask.to(dtype), vertex, hn, thresh=thresh, seed=int(rng.integers(0, 2 ** 62)),
+              img_base=int(rng.integers(0, 1000)), max_num=max_num, min_num=int(rng.integers(1, 9)))
+
+
 def test_v3_seed_follows_torch_manual_seed(pvb):
     mask, vertex, _ = _inputs(pvb, "tiny", seed=11)
     torch.manual_seed(5)

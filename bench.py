@@ -37,9 +37,10 @@ WORKLOAD = "cfg2"
 HN = 512
 THRESH = 0.99
 KERNELS_PER_STEP = 6   # mask_bits, thin_scan, gather, generate, vote, refit
-# dram__bytes_read.sum + dram__bytes_write.sum of one vote_kernel launch on this workload, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_summary.txt): 39 394 304 + 256 bytes
-VOTE_KERNEL_DRAM_BYTES = 39394560
+# dram__bytes_read.sum + dram__bytes_write.sum of one vote-kernel launch on this workload, from the committed
+# `ncu --set full` capture of vote_mma_kernel (profiles/r01_ncu_summary.txt): 39 410 432 + 512 bytes
+# (the FP32-pipe vote_kernel it replaced as the default at hn >= 512: 39 394 304 + 256)
+VOTE_KERNEL_DRAM_BYTES = 39410944
 
 
 def _env_int(name, default):
@@ -358,16 +359,18 @@ def run_ours(args):
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None,
                 "traffic": args.traffic if args.traffic is not None else VOTE_KERNEL_DRAM_BYTES,
-                "kernel": "pvb::vote_kernel<4,128,8,512>", "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
+                "kernel": "pvb::vote_mma_kernel<8,8,2,1024>", "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
                 "peak_source": peak_src,
-                "note": "the vote kernel is FP32-issue bound by construction (hn inlier tests per 16 loaded bytes); "
+                "note": "the vote kernel is issue/tensor-pipe bound by construction (hn inlier tests per 16 loaded bytes); "
                         "see 'alu' and DESIGN.md",
             },
             "alu": {"inlier_tests_per_step": tests, "tests_per_s_vote_kernel": tests / (vote_ms * 1e-3) if vote_ms else None,
                     "lane_ops_peak_per_s": 148 * 128 * sm_mhz * 1e6,
-                    "sass_instr_per_test": 7.1,
-                    "note": "454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
-                            "24 LDS); tools/microbench.cu bounds this mix at 610 cycles/block/SMSP => ~4.2 T tests/s"},
+                    "sass_instr_per_test": 3.4,
+                    "note": "tensor path: 217 SASS instr per warp per 2 x (16 pixels x 64 hypotheses) = 32 HMMA.1688.F32.TF32 "
+                            "(tf32x3 split) + 64 FADD + 64 LEA.HI + 32 FMNMX3 + 4 LDS.128; HMMA issues every 8 cycles per "
+                            "SMSP (tools/microbench3.cu) => 16 HMMA + ~96 ALU/FMA issue slots per 1024 tests; the FP32-pipe "
+                            "kernel it replaces at hn >= 512 needs 7.1 instr/test (454 per 64 tests) and runs 8 % slower"},
             "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
             "extras": extras,
         }

@@ -471,7 +471,7 @@ PVB_API int pvb_set_host_mode(int32_t zero_copy) { g_host_zero_copy = zero_copy 
 
 PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant)
 {
-    if (vote_variant < 0 || vote_variant > 2) return fail(PVB_ERR_INVALID, "vote_variant must be 0..2");
+    if (vote_variant < 0 || vote_variant > 5) return fail(PVB_ERR_INVALID, "vote_variant must be 0..5");
     (void)vote_chunk;
     set_vote_tuning(vote_variant);
     return PVB_OK;

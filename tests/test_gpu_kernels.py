@@ -113,6 +113,66 @@ def test_vote_count_adversarial(pvb, oracle):
     assert np.array_equal(got, want)
 
 
+@pytest.fixture
+def vote_variant():
+    """Force one vote kernel (include/pvnet_vote_b200.h, pvb_set_tuning) for the duration of a test."""
+    from clean_pvnet_b200 import _lib
+    lib = _lib.load()
+
+    def force(v):
+        _lib.check(lib.pvb_set_tuning(0, v))
+    yield force
+    _lib.check(lib.pvb_set_tuning(0, 0))
+
+
+@pytest.mark.parametrize("variant", [1, 3, 4, 5])
+@pytest.mark.parametrize("tn,vn,hn,seed,thresh", [
+    (1500, 2, 24, 20, 0.99), (2100, 3, 64, 21, 0.99), (3000, 2, 130, 22, 0.999), (1111, 2, 512, 23, 0.99),
+    (2500, 1, 520, 24, 0.9), (1030, 2, 1100, 25, 0.99), (17, 1, 8, 26, 0.99), (1024, 1, 64, 27, 0.5)])
+def test_every_vote_kernel_matches_oracle(pvb, oracle, vote_variant, variant, tn, vn, hn, seed, thresh):
+    """Both vote kernels (FP32-pipe and tensor-path, every tile size) at hypothesis counts on both sides of the default
+    switch-over, with partial hypothesis groups, warp teams (hn < 512 on the tensor path) and partial pixel tiles."""
+    direct, coords, idxs, _ = field_case(tn, vn, hn, seed)
+    hyp = oracle.generate_hypothesis(direct, coords, idxs)
+    want = oracle.vote_count(direct, coords, hyp, thresh)
+    vote_variant(variant)
+    got = pvb.ransac_voting.vote_count(*cuda(direct, coords, hyp), thresh).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("variant", [1, 4, 5])
+def test_every_vote_kernel_adversarial(pvb, oracle, vote_variant, variant):
+    """The adversarial case above under each kernel, plus hypotheses/pixels that force the exact path wholesale."""
+    rng = np.random.default_rng(12)
+    tn, vn, hn = 1500, 2, 200
+    coords = np.round(rng.uniform(0, 640, size=(tn, 2))).astype(np.float32)
+    ang = rng.uniform(0, 2 * np.pi, size=(tn, vn))
+    direct = np.stack([np.cos(ang), np.sin(ang)], axis=-1).astype(np.float32)
+    scale = rng.choice([1.0, 1e-7, 1.1e-6, 1e4, 1e19, 0.0], size=(tn, vn, 1), p=[.7, .05, .05, .1, .05, .05])
+    direct = (direct * scale).astype(np.float32)
+    direct[5, 0] = [np.nan, 1.0]
+    direct[6, 1] = [np.inf, 0.0]
+    coords[7] = [1e7, -3e6]          # far outside its tile's box: that tile's records go the exact way
+    hyp = rng.uniform(-200, 900, size=(hn, vn, 2)).astype(np.float32)
+    hyp[:32, 0] = coords[:32]
+    th = np.arccos(np.float32(0.99))
+    for j in range(32, 160):
+        t = rng.integers(0, tn)
+        k = j % vn
+        a = np.arctan2(direct[t, k, 1], direct[t, k, 0]) + rng.choice([-1, 1]) * th * rng.choice([1.0, 1 + 1e-7, 1 - 1e-7])
+        r = rng.choice([0.5, 3.0, 50.0, 700.0, 1e5])
+        hyp[j, k] = coords[t] + r * np.array([np.cos(a), np.sin(a)], dtype=np.float64)
+    hyp[160:170] *= 1e6
+    hyp[170:174] *= 1e20
+    hyp[174, 0] = [np.nan, 3.0]
+    hyp[175, 1] = [np.inf, -np.inf]
+    with np.errstate(all="ignore"):
+        want = oracle.vote_count(direct, coords, hyp, 0.99)
+    vote_variant(variant)
+    got = pvb.ransac_voting.vote_count(*cuda(direct, coords, hyp), 0.99).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_vote_count_empty_and_ragged(pvb, oracle):
     direct, coords, idxs, _ = field_case(257, 5, 129, 9)
     hyp = oracle.generate_hypothesis(direct, coords, idxs)

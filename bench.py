@@ -37,10 +37,11 @@ WORKLOAD = "cfg2"
 HN = 512
 THRESH = 0.99
 KERNELS_PER_STEP = 6   # mask_bits, thin_scan, gather, generate, vote, refit
-# dram__bytes_read.sum + dram__bytes_write.sum of one vote-kernel launch on this workload, from the committed
-# `ncu --set full` capture of vote_mma_kernel (profiles/r01_ncu_summary.txt): 39 410 432 + 512 bytes
-# (the FP32-pipe vote_kernel it replaced as the default at hn >= 512: 39 394 304 + 256)
-VOTE_KERNEL_DRAM_BYTES = 39410944
+# dram__bytes_read.sum + dram__bytes_write.sum of one vote_kernel launch on this workload, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_summary.txt): 39 394 304 + 256 bytes
+VOTE_KERNEL_DRAM_BYTES = 39394560
+# the opt-in tensor-path experiment (PVB_VOTE_VARIANT=4|5; not the shipped default): 39 408 640 + 3 072 bytes
+VOTE_MMA_KERNEL_DRAM_BYTES = 39411712
 
 
 def _env_int(name, default):
@@ -192,6 +193,7 @@ def run_ours(args):
     from clean_pvnet_b200 import _lib, parallel, synth
 
     rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    tensor_path = _env_int("PVB_VOTE_VARIANT", 0) >= 4     # opt-in experiment (tooling); the shipped default is 0
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -358,19 +360,22 @@ def run_ours(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None,
-                "traffic": args.traffic if args.traffic is not None else VOTE_KERNEL_DRAM_BYTES,
-                "kernel": "pvb::vote_mma_kernel<8,8,2,1024>", "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
+                "traffic": args.traffic if args.traffic is not None else
+                (VOTE_MMA_KERNEL_DRAM_BYTES if tensor_path else VOTE_KERNEL_DRAM_BYTES),
+                "kernel": "pvb::vote_mma_kernel<8,8,2,1024> (opt-in experiment)" if tensor_path else "pvb::vote_kernel<4,128,8,512,4>",
+                "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
                 "peak_source": peak_src,
-                "note": "the vote kernel is issue/tensor-pipe bound by construction (hn inlier tests per 16 loaded bytes); "
+                "note": "the vote kernel is FP32-issue bound by construction (hn inlier tests per 16 loaded bytes); "
                         "see 'alu' and DESIGN.md",
             },
             "alu": {"inlier_tests_per_step": tests, "tests_per_s_vote_kernel": tests / (vote_ms * 1e-3) if vote_ms else None,
                     "lane_ops_peak_per_s": 148 * 128 * sm_mhz * 1e6,
-                    "sass_instr_per_test": 3.4,
-                    "note": "tensor path: 217 SASS instr per warp per 2 x (16 pixels x 64 hypotheses) = 32 HMMA.1688.F32.TF32 "
-                            "(tf32x3 split) + 64 FADD + 64 LEA.HI + 32 FMNMX3 + 4 LDS.128; HMMA issues every 8 cycles per "
-                            "SMSP (tools/microbench3.cu) => 16 HMMA + ~96 ALU/FMA issue slots per 1024 tests; the FP32-pipe "
-                            "kernel it replaces at hn >= 512 needs 7.1 instr/test (454 per 64 tests) and runs 8 % slower"},
+                    "sass_instr_per_test": 3.4 if tensor_path else 7.1,
+                    "note": ("opt-in tensor-path experiment: 217 SASS instr per warp per 2 x (16 pixels x 64 hypotheses) = 32 "
+                             "HMMA.1688.F32.TF32 (tf32x3 split) + 64 FADD + 64 LEA.HI + 32 FMNMX3 + 4 LDS.128; HMMA issues "
+                             "every 8 cycles per SMSP (tools/microbench3.cu)") if tensor_path else
+                            ("454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
+                             "24 LDS); tools/microbench.cu bounds this mix at 610 cycles/block/SMSP => ~4.2 T tests/s")},
             "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
             "extras": extras,
         }

@@ -20,6 +20,9 @@
 //     (tools/band_check.c) bounds every rounding difference between the two; blocks
 //     whose smallest |m| falls inside it are re-evaluated -- warp-cooperatively -- with the
 //     reference's exact operation sequence (vote_exact).  Counts equal the reference's.
+//
+// vote_mma_kernel (further down) is an opt-in experiment, not the shipped path: the same margin through mma.sync (tf32 x 3
+// split) -- see the comment above it, DESIGN.md 4.2 and profiles/r01_vote_tuning.md.
 #include <math_constants.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -605,10 +608,9 @@ ConeParams make_cone(float thresh)
     return c;
 }
 
-// 0 -> default: tensor-path kernel (mma.sync tf32x3, 64 hypotheses per warp, 8 warps, 1024-pixel tile, 2 CTAs/SM) when
-//      hn >= 512, FP32-pipe kernel (512-pixel tile) below;
-// 1 / 2 / 3 -> FP32-pipe kernel for every hn with a 512 / 256 / 1024-pixel tile;
-// 4 / 5 -> tensor-path kernel for every hn with a 1024 / 512-pixel tile
+// 0 / 1 -> FP32-pipe kernel, 512-pixel tile (the default); 2 / 3 -> same with a 256 / 1024-pixel tile;
+// 4 / 5 -> experimental tensor-path kernel (mma.sync tf32x3, 64 hypotheses per warp, 8 warps, 2 CTAs/SM) with a
+//          1024 / 512-pixel tile -- opt-in only, see launch_vote
 static int g_vote_variant = 0;
 
 void set_vote_tuning(int variant) { g_vote_variant = variant; }
@@ -640,9 +642,10 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
         }                                                                                                   \
         kern<<<g, (NWARP) * 32, smem, st>>>(p, gpc);                                                        \
     } while (0)
-    // default: tensor path from 512 hypotheses per keypoint (measured 8-9 % faster at hn = 512 / 2048, 7 % slower at
-    // hn = 128 where half of each CTA's warps only split the pixel blocks; profiles/r01_vote_tuning.md)
-    const bool mma = (g_vote_variant == 0) ? (a.hn >= 512) : (g_vote_variant >= 4);
+    // The tensor path is opt-in (variants 4/5): BASELINE.json's north star rules tensor cores out for this path, so the
+    // shipped default is the FP32-pipe kernel for every hn.  Measured for the record (profiles/r01_vote_tuning.md):
+    // 8-9 % faster at hn = 512 / 2048, 7 % slower at hn = 128.
+    const bool mma = g_vote_variant >= 4;
     if (mma) {
         if (g_vote_variant == 5) PVB_VOTE_MMA(8, 8, 2, 512);
         else PVB_VOTE_MMA(8, 8, 2, 1024);

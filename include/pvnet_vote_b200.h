@@ -194,9 +194,10 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
 /* Tuning switch (tooling; process-wide).  reserved: pass 0.  vote_variant selects the vote kernel:
- * 0 = default (tensor-path kernel from 512 hypotheses per keypoint, FP32-pipe kernel below),
- * 1 / 2 / 3 = FP32-pipe kernel with a 512 / 256 / 1024-pixel tile, 4 / 5 = tensor-path kernel with a 1024 / 512-pixel
- * tile.  Results do not depend on it (every variant reproduces the reference's inlier counts). */
+ * 0 = default = 1 = FP32-pipe kernel with a 512-pixel tile; 2 / 3 = the same with a 256 / 1024-pixel tile;
+ * 4 / 5 = experimental tensor-path kernel (mma.sync, tf32 x 3 split) with a 1024 / 512-pixel tile -- opt-in only: the
+ * path's specification excludes tensor cores, the variant exists to document what they would buy.
+ * Results do not depend on the variant (every one reproduces the reference's inlier counts). */
 PVB_API int pvb_set_tuning(int32_t reserved, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);
 PVB_API int pvb_profile_read(double *ms, int32_t n);

@@ -295,6 +295,17 @@ def run_ours(args):
                                                img_base=rank * B), 30)
     except Exception as e:
         extras["error"] = str(e)
+    try:
+        # SURVEY 8f rows 2+3: the un_pnp tail for this batch -- cov -> inv(sqrtm(cov)) weights, then the batched LM pose
+        # refinement (one warp per image), from the keypoints / covariances the voting layer just produced
+        kp2d, var = pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, seed=7, img_base=rank * B)
+        model = torch.rand((K, 3), device=dev, dtype=torch.float64) * 0.2 - 0.1
+        cam = torch.tensor([[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]], device=dev, dtype=torch.float64)
+        init = torch.tensor([0.1, -0.2, 0.3, 0.0, 0.0, 0.9], device=dev, dtype=torch.float64).repeat(B, 1)
+        extras["un_pnp_tail_ms"] = timed(
+            lambda: pvb.uncertainty_pnp_batch(kp2d, pvb.uncertainty_pnp_weights(var), model, cam, init), 20)
+    except Exception as e:
+        extras["un_pnp_error"] = str(e)
 
     # ---- end-to-end: pinned host inputs -> H2D -> kernels -> D2H, through the public host entry
     mh, vh = mask.cpu().pin_memory(), vertex.contiguous().cpu().pin_memory()

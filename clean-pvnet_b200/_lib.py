@@ -37,6 +37,13 @@ class PvbLayout(ctypes.Structure):
                     ("refit_splits", ctypes.c_int32)]
 
 
+class PvbPnpOptions(ctypes.Structure):
+    """== struct pvb_pnp_options (include/pvnet_vote_b200.h)"""
+    _fields_ = [("max_num_iterations", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("function_tolerance", ctypes.c_double), ("gradient_tolerance", ctypes.c_double),
+                ("parameter_tolerance", ctypes.c_double)]
+
+
 # every symbol include/pvnet_vote_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _sz, _f = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t, ctypes.c_float
 _dp, _lp = ctypes.POINTER(PvbDesc), ctypes.POINTER(PvbLayout)
@@ -49,6 +56,8 @@ SIGNATURES = {
     "pvb_decode_v3": (ctypes.c_int, [_dp, _vp, _i32, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pvb_estimate_voting_distribution": (ctypes.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pvb_uncertainty_weights": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
+    "pvb_uncertainty_pnp": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_int64, ctypes.c_int64,
+                                           ctypes.c_void_p, _vp]),
     "pvb_read_status": (ctypes.c_int, [_dp, _vp, _vp]),
     "pvb_host_scratch_bytes": (_sz, [_dp, _i32]),
     "pvb_ransac_voting_v3_host": (ctypes.c_int, [_dp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),

@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "select.cu", "vote.cu", "compat.cu"]
+SOURCES = ["api.cu", "select.cu", "vote.cu", "compat.cu", "pnp.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "pvnet_vote_b200.h")]
 LIB = os.path.join(HERE, "libpvnet_vote_b200.so")
 

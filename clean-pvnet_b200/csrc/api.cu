@@ -307,6 +307,29 @@ PVB_API int pvb_uncertainty_weights(const float *cov, float *weights, int32_t n,
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "pnp weights kernel");
 }
 
+PVB_API int pvb_uncertainty_pnp(const double *pts2d, const double *pts3d, const double *wgt2d, const double *K,
+                                const double *init_rt, double *result_rt, int32_t *info, int32_t n, int32_t pn,
+                                int64_t pts3d_stride, int64_t k_stride, const pvb_pnp_options *options, pvb_stream_t stream)
+{
+    if (n < 0) return fail(PVB_ERR_INVALID, "n < 0");
+    if (pn < 1) return fail(PVB_ERR_INVALID, "pn must be >= 1 (got %d)", pn);
+    if (n && (!pts2d || !pts3d || !wgt2d || !K || !init_rt || !result_rt)) return fail(PVB_ERR_INVALID, "NULL tensor");
+    if (pts3d_stride < 0 || k_stride < 0) return fail(PVB_ERR_INVALID, "negative stride");
+    PnpArgs a;
+    a.pts2d = pts2d; a.pts3d = pts3d; a.wgt2d = wgt2d; a.K = K; a.init_rt = init_rt; a.result_rt = result_rt; a.info = info;
+    a.n = n; a.pn = pn; a.pts3d_stride = pts3d_stride; a.k_stride = k_stride;
+    a.max_num_iterations = 50; a.function_tolerance = 1e-6; a.gradient_tolerance = 1e-10; a.parameter_tolerance = 1e-8;
+    if (options) {
+        if (options->max_num_iterations < 0 || !(options->function_tolerance >= 0.0) || !(options->gradient_tolerance >= 0.0) ||
+            !(options->parameter_tolerance >= 0.0))
+            return fail(PVB_ERR_INVALID, "pvb_pnp_options: negative or NaN entry");
+        a.max_num_iterations = options->max_num_iterations; a.function_tolerance = options->function_tolerance;
+        a.gradient_tolerance = options->gradient_tolerance; a.parameter_tolerance = options->parameter_tolerance;
+    }
+    cudaError_t e = launch_pnp(a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "uncertainty pnp kernel");
+}
+
 PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream)
 {
     pvb_layout L;

@@ -59,6 +59,22 @@ cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_c
 // inv(sqrtm(cov)) packed (wxx,wxy,wyy): cov [n][2][2] -> w [n][3]
 cudaError_t launch_pnp_weights(const float *cov, float *w, int n, cudaStream_t st);
 
+// batched uncertainty-PnP refinement (pnp.cu): n problems of pn points, fp64 like the reference
+struct PnpArgs {
+    const double *pts2d;      // [n][pn][2]
+    const double *pts3d;      // [pn][3], problem p at pts3d + p*pts3d_stride (0: shared)
+    const double *wgt2d;      // [n][pn][3]  (wxx, wxy, wyy)
+    const double *K;          // [3][3] row-major, problem p at K + p*k_stride (0: shared)
+    const double *init_rt;    // [n][6]
+    double *result_rt;        // [n][6]
+    int *info;                // optional [n][2]: iterations, termination code
+    int n, pn;
+    long long pts3d_stride, k_stride;
+    int max_num_iterations;
+    double function_tolerance, gradient_tolerance, parameter_tolerance;
+};
+cudaError_t launch_pnp(const PnpArgs &a, cudaStream_t st);
+
 // twins of the reference extension on its own layouts
 cudaError_t launch_compat_generate(const float *direct, const float *coords, const int32_t *idxs, float *hyp,
                                    int tn, int vn, int hn, bool vanishing, cudaStream_t st);

@@ -162,6 +162,26 @@ PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask
  * The result is what un_pnp_utils.uncertainty_pnp (lib/csrc/uncertainty_pnp/un_pnp_utils.py:6) takes as weights_2d. */
 PVB_API int pvb_uncertainty_weights(const float *cov, float *weights, int32_t n, pvb_stream_t stream);
 
+/* Batched twin of the reference's C entry `uncertainty_pnp(pts2d, pts3d, wgt2d, K, init_rt, result_rt, pn)`
+ * (lib/csrc/uncertainty_pnp/src/ext.h:1-9, uncertainty_pnp.cpp:61-92; bound through cffi by un_pnp_utils.py:49-53): refines
+ * n poses (angle-axis + translation, 6 doubles) by minimising the weighted reprojection error of pn points each with the
+ * Levenberg-Marquardt trust-region loop and the default options of Ceres Solver 2.0 (the reference's minimiser; DESIGN.md
+ * section 8 says what of it is and is not pinned).  One warp per problem, fp64 like the reference.
+ * All pointers are DEVICE memory: pts2d [n,pn,2], wgt2d [n,pn,3] = (wxx,wxy,wyy), init_rt / result_rt [n,6],
+ * pts3d [pn,3] and K [3,3] (row-major) per problem at pts3d + p*pts3d_stride / K + p*k_stride (strides in doubles; 0 = one
+ * array shared by all problems), info optional int32 [n,2] = (iterations, termination: 1 gradient, 2 parameter, 3 function
+ * tolerance, 4 trust region collapsed, 5 iteration limit, 6 five invalid steps in a row).  options NULL = Ceres defaults. */
+typedef struct pvb_pnp_options {
+    int32_t max_num_iterations;       /* 50   */
+    int32_t reserved;                 /* 0    */
+    double function_tolerance;        /* 1e-6 */
+    double gradient_tolerance;        /* 1e-10 */
+    double parameter_tolerance;       /* 1e-8 */
+} pvb_pnp_options;
+PVB_API int pvb_uncertainty_pnp(const double *pts2d, const double *pts3d, const double *wgt2d, const double *K,
+                                const double *init_rt, double *result_rt, int32_t *info, int32_t n, int32_t pn,
+                                int64_t pts3d_stride, int64_t k_stride, const pvb_pnp_options *options, pvb_stream_t stream);
+
 /* Reads the sticky status word of a workspace (synchronises `stream`). */
 PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream);
 

@@ -1,0 +1,142 @@
+"""GPU: the batched uncertainty-PnP kernel (pvb_uncertainty_pnp, csrc/pnp.cu) against the oracle (oracle/pnp_oracle.py).
+
+Tolerances (float64 throughout): where kernel and oracle take the same number of iterations and stop for the same reason the
+poses agree to 1e-9 (the warp's butterfly sum and the oracle's BLAS sum differ in the last bits only); a last-bit difference
+may flip a convergence test once in a while, which moves the result by at most the slack Ceres' function_tolerance = 1e-6
+leaves (<= 2e-4 in pose units, tests/test_pnp_oracle.py) -- allowed for at most 5 % of the problems.  With tight
+tolerances both converge to the optimum and must agree to 1e-8 always."""
+import numpy as np
+import pytest
+import torch
+
+from util import pnp_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def po():
+    import pnp_oracle
+    return pnp_oracle
+
+
+def _batch(cases):
+    f = lambda i: torch.from_numpy(np.stack([c[i] for c in cases])).cuda()   # noqa: E731
+    return f(0), f(1), f(2), f(3), f(4)
+
+
+def test_batch_matches_oracle_default_options(pvb, po):
+    cases = [pnp_case(400 + s, pn=9, noise=2.0, pert=(0.3, 0.1) if s % 3 == 0 else (0.05, 0.02)) for s in range(64)]
+    uv, p3, W, K, init = _batch(cases)
+    rt, info = pvb.uncertainty_pnp_batch(uv, W, p3, K, init, return_info=True)
+    rt, info = rt.cpu().numpy(), info.cpu().numpy()
+    same = 0
+    for i, c in enumerate(cases):
+        want, oi = po.uncertainty_pnp(*c[:5], return_info=True)
+        if (info[i, 0], info[i, 1]) == (oi["iterations"], oi["termination"]):
+            same += 1
+            assert np.abs(rt[i] - want).max() < 1e-9, i
+        else:
+            assert np.abs(rt[i] - want).max() < 2e-4, i
+    assert same >= 61
+
+
+@pytest.mark.parametrize("pn", [5, 9, 17, 40])
+def test_tight_tolerances_reach_the_optimum(pvb, po, pn):
+    cases = [pnp_case(500 + s, pn=pn, noise=1.5, pert=(0.2, 0.08)) for s in range(8)]
+    uv, p3, W, K, init = _batch(cases)
+    rt = pvb.uncertainty_pnp_batch(uv, W, p3, K, init, max_num_iterations=200, function_tolerance=1e-16,
+                                   gradient_tolerance=1e-14, parameter_tolerance=1e-16).cpu().numpy()
+    for i, c in enumerate(cases):
+        want = po.uncertainty_pnp(*c[:5], max_num_iterations=200, function_tolerance=1e-16, gradient_tolerance=1e-14,
+                                  parameter_tolerance=1e-16)
+        assert np.abs(rt[i] - want).max() < 1e-8, (pn, i)
+
+
+def test_shared_model_points_and_intrinsics(pvb, po):
+    """The production shape: one object model and one camera for the whole batch (stride 0), fp32 inputs as the voting
+    layer and pvb_uncertainty_weights produce them."""
+    base = pnp_case(600, pn=9)
+    cases = []
+    for s in range(16):
+        c = pnp_case(601 + s, pn=9, noise=1.0)
+        rng = np.random.default_rng(700 + s)
+        # re-project the SHARED model points with this case's pose
+        aa, t = c[5][:3], c[5][3:]
+        R = po.rodrigues(aa)
+        cam = base[1] @ R.T + t
+        uv = np.stack([base[3][0, 0] * cam[:, 0] / cam[:, 2] + base[3][0, 2], base[3][1, 1] * cam[:, 1] / cam[:, 2] + base[3][1, 2]], 1)
+        uv += rng.normal(size=uv.shape)
+        cases.append((uv.astype(np.float32).astype(np.float64), base[1], c[2].astype(np.float32).astype(np.float64), base[3], c[4]))
+    uv = torch.from_numpy(np.stack([c[0] for c in cases])).float().cuda()
+    W = torch.from_numpy(np.stack([c[2] for c in cases])).float().cuda()
+    init = torch.from_numpy(np.stack([c[4] for c in cases])).cuda()
+    rt, info = pvb.uncertainty_pnp_batch(uv, W, torch.from_numpy(base[1]).cuda(), torch.from_numpy(base[3]).cuda(), init,
+                                         return_info=True)
+    rt, info = rt.cpu().numpy(), info.cpu().numpy()
+    for i, c in enumerate(cases):
+        want, oi = po.uncertainty_pnp(*c, return_info=True)
+        tol = 1e-9 if (info[i, 0], info[i, 1]) == (oi["iterations"], oi["termination"]) else 2e-4
+        assert np.abs(rt[i] - want).max() < tol, i
+    # per-problem copies of the same arrays give the same bits as the shared ones
+    rt2 = pvb.uncertainty_pnp_batch(uv, W, torch.from_numpy(base[1]).cuda().expand(16, 9, 3).contiguous(),
+                                    torch.from_numpy(base[3]).cuda().expand(16, 3, 3).contiguous(), init)
+    assert np.array_equal(rt2.cpu().numpy(), rt)
+
+
+def test_degenerate_problems_in_a_batch(pvb, po):
+    good = pnp_case(800, pn=9)[:5]
+    zero_w = (good[0], good[1], np.zeros_like(good[2]), good[3], good[4])
+    at_opt = pnp_case(801, pn=9, noise=0.0)
+    at_opt = (at_opt[0], at_opt[1], at_opt[2], at_opt[3], at_opt[5])
+    nan_w = (good[0], good[1], good[2].copy(), good[3], good[4])
+    nan_w[2][2, 0] = np.nan
+    behind = (good[0], good[1], good[2], good[3], good[4].copy())
+    behind[4][5] = -0.05
+    cases = [good, zero_w, at_opt, nan_w, behind]
+    uv, p3, W, K, init = _batch(cases)
+    rt, info = pvb.uncertainty_pnp_batch(uv, W, p3, K, init, return_info=True)
+    rt, info = rt.cpu().numpy(), info.cpu().numpy()
+    for i, c in enumerate(cases[:4]):
+        with np.errstate(all="ignore"):
+            want, oi = po.uncertainty_pnp(*c[:5], return_info=True)
+        if i == 0 and (info[i, 0], info[i, 1]) != (oi["iterations"], oi["termination"]):
+            assert np.abs(rt[i] - want).max() < 2e-4           # a last-bit flip of a convergence test (see module docstring)
+            continue
+        assert (info[i, 0], info[i, 1]) == (oi["iterations"], oi["termination"]), i
+        assert np.allclose(rt[i], want, rtol=1e-9, atol=1e-9, equal_nan=True), i
+    # points behind the camera: a long, ill-conditioned descent (28 iterations in the oracle) whose path depends on the last
+    # bits of the sums -- only required to terminate with a valid code and without touching its neighbours
+    assert 1 <= info[4, 1] <= 6 and 0 <= info[4, 0] <= 50
+    assert np.array_equal(rt[1], zero_w[4]) and np.array_equal(rt[3], nan_w[4])      # untouched initial poses
+    empty = pvb.uncertainty_pnp_batch(uv[:0], W[:0], p3[:0], K[:0], init[:0])
+    assert empty.shape == (0, 6)
+
+
+def test_reference_python_twins(pvb, po):
+    """un_pnp_utils.uncertainty_pnp / _v2 twins: OpenCV P3P initialisation exactly as the reference does it, refinement on the
+    GPU; compared with the oracle started from the same P3P pose."""
+    cv2 = pytest.importorskip("cv2")
+    uv, p3, W, K, _, true_rt = pnp_case(900, pn=9, noise=0.5)
+    Rt = pvb.un_pnp.uncertainty_pnp(uv, W, p3, K)
+    assert Rt.shape == (3, 4)
+    idxs = np.argsort(W[:, 0] + W[:, 1])[-4:]
+    _, r_exp, t = cv2.solvePnP(np.expand_dims(p3[idxs], 0), np.expand_dims(uv[idxs], 0), K, np.zeros((8, 1)), None, None, False,
+                               flags=cv2.SOLVEPNP_P3P)
+    want = po.uncertainty_pnp(uv, p3, W, K, np.concatenate([r_exp, t], 0).reshape(6))
+    assert np.abs(Rt[:, :3] - po.rodrigues(want[:3])).max() < 1e-6 and np.abs(Rt[:, 3] - want[3:]).max() < 1e-6
+    assert np.abs(Rt[:, 3] - true_rt[3:]).max() < 0.05                                   # and it is a sensible pose
+    cov = np.stack([np.eye(2) * s for s in np.linspace(0.5, 3.0, 9)])
+    Rt2 = pvb.un_pnp.uncertainty_pnp_v2(uv, cov, p3, K)
+    assert Rt2.shape == (3, 4) and np.abs(Rt2[:, 3] - true_rt[3:]).max() < 0.05
+    Rt4 = pvb.un_pnp.uncertainty_pnp(uv[:4], W[:4], p3[:4], K)                            # pn == 4: the P3P pose itself
+    assert Rt4.shape == (3, 4) and np.isfinite(Rt4).all()
+
+
+def test_input_checks(pvb):
+    uv = torch.zeros((2, 9, 2), device="cuda")
+    with pytest.raises(RuntimeError):
+        pvb.uncertainty_pnp_batch(uv.cpu(), uv, uv, uv, uv)
+    with pytest.raises(RuntimeError):
+        pvb.uncertainty_pnp_batch(uv, torch.zeros((2, 9, 2), device="cuda"), torch.zeros((9, 3), device="cuda"),
+                                  torch.zeros((3, 3), device="cuda"), torch.zeros((2, 6), device="cuda"))

@@ -14,7 +14,7 @@ from . import ransac_voting_gpu  # noqa: F401
 from . import decode  # noqa: F401
 from .decode import decode_keypoint, uncertainty_pnp_weights  # noqa: F401
 from . import uncertainty_pnp as un_pnp  # noqa: F401
-from .uncertainty_pnp import uncertainty_pnp_batch  # noqa: F401
+from .uncertainty_pnp import uncertainty_pnp_batch, p3p_init_batch  # noqa: F401
 from .ransac_voting_gpu import (  # noqa: F401
     estimate_voting_distribution_with_mean,
     ransac_voting_layer,
@@ -26,5 +26,5 @@ from .ransac_voting_gpu import (  # noqa: F401
 __all__ = [
     "ransac_voting_layer", "ransac_voting_layer_v3", "estimate_voting_distribution_with_mean",
     "ransac_voting_layer_v3_host", "install_as_reference_module", "ransac_voting", "ransac_voting_gpu",
-    "decode_keypoint", "uncertainty_pnp_weights", "un_pnp", "uncertainty_pnp_batch",
+    "decode_keypoint", "uncertainty_pnp_weights", "un_pnp", "uncertainty_pnp_batch", "p3p_init_batch",
 ]

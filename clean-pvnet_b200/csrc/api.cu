@@ -330,6 +330,22 @@ PVB_API int pvb_uncertainty_pnp(const double *pts2d, const double *pts3d, const 
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "uncertainty pnp kernel");
 }
 
+PVB_API int pvb_uncertainty_pnp_init(const double *pts2d, const double *pts3d, const double *wgt2d, const double *K,
+                                     double *init_rt, int32_t n, int32_t pn, int64_t pts3d_stride, int64_t k_stride,
+                                     pvb_stream_t stream)
+{
+    if (n < 0) return fail(PVB_ERR_INVALID, "n < 0");
+    if (pn < 4) return fail(PVB_ERR_INVALID, "P3P needs pn >= 4 (got %d)", pn);
+    if (n && (!pts2d || !pts3d || !wgt2d || !K || !init_rt)) return fail(PVB_ERR_INVALID, "NULL tensor");
+    if (pts3d_stride < 0 || k_stride < 0) return fail(PVB_ERR_INVALID, "negative stride");
+    PnpArgs a;
+    a.pts2d = pts2d; a.pts3d = pts3d; a.wgt2d = wgt2d; a.K = K; a.init_rt = nullptr; a.result_rt = init_rt; a.info = nullptr;
+    a.n = n; a.pn = pn; a.pts3d_stride = pts3d_stride; a.k_stride = k_stride;
+    a.max_num_iterations = 0; a.function_tolerance = a.gradient_tolerance = a.parameter_tolerance = 0.0;
+    cudaError_t e = launch_p3p_init(a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "p3p init kernel");
+}
+
 PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream)
 {
     pvb_layout L;

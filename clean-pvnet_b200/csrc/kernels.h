@@ -74,6 +74,8 @@ struct PnpArgs {
     double function_tolerance, gradient_tolerance, parameter_tolerance;
 };
 cudaError_t launch_pnp(const PnpArgs &a, cudaStream_t st);
+// initial poses by P3P on the 4 best-weighted points (uses pts2d/pts3d/wgt2d/K, writes result_rt)
+cudaError_t launch_p3p_init(const PnpArgs &a, cudaStream_t st);
 
 // twins of the reference extension on its own layouts
 cudaError_t launch_compat_generate(const float *direct, const float *coords, const int32_t *idxs, float *hyp,

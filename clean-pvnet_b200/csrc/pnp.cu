@@ -5,9 +5,11 @@
 // evaluates their residuals and 2x6 Jacobians (pnp_core.cuh) and the warp adds the 28 numbers of the normal equations with
 // an XOR butterfly (every lane ends with the same bits, so all lanes run the identical trust-region state machine without
 // divergence or broadcasts).  Everything is fp64 like the reference.  Latency-bound by design: ~10 evaluations per problem.
+#include <math_constants.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "pnp_core.cuh"
+#include "p3p_core.cuh"
 
 namespace pvb {
 
@@ -53,6 +55,45 @@ pnp_kernel(PnpArgs a)
     }
     if (lane < 6) a.result_rt[(size_t)prob * 6 + lane] = st.x[lane];
     if (a.info && lane == 0) { a.info[2 * prob] = st.iterations; a.info[2 * prob + 1] = st.code; }
+}
+
+// Initial poses: the reference's recipe (un_pnp_utils.py:25-31) -- the four keypoints with the largest wxx + wxy, ascending;
+// P3P on the first three, the best-weighted one picks the root (p3p_core.cuh).  One thread per problem: the work is a
+// short scalar chain (quartic, <= 4 alignments).  No admissible solution -> NaN pose, which is what OpenCV hands the
+// reference in that case; the refinement then stops at once with that pose.
+__global__ void __launch_bounds__(64)
+p3p_init_kernel(PnpArgs a)
+{
+    const int prob = blockIdx.x * 64 + threadIdx.x;
+    if (prob >= a.n) return;
+    const double *p2 = a.pts2d + (size_t)prob * a.pn * 2;
+    const double *p3 = a.pts3d + (size_t)prob * a.pts3d_stride;
+    const double *w = a.wgt2d + (size_t)prob * a.pn * 3;
+    const double *K = a.K + (size_t)prob * a.k_stride;
+    const double cam[4] = { K[0], K[4], K[2], K[5] };
+    int idx[4];
+    p3p_select4(w, a.pn, idx);
+    double X[4][3], x2[4][2], rt[6];
+    const double nan = CUDART_NAN;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rt[i] = nan;
+    bool ok = a.pn >= 4;
+    if (ok) {
+        for (int r = 0; r < 4; ++r) {
+            for (int c = 0; c < 3; ++c) X[r][c] = p3[3 * idx[r] + c];
+            x2[r][0] = p2[2 * idx[r]]; x2[r][1] = p2[2 * idx[r] + 1];
+        }
+        p3p_solve4(X, x2, cam, rt);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.result_rt[(size_t)prob * 6 + i] = rt[i];
+}
+
+cudaError_t launch_p3p_init(const PnpArgs &a, cudaStream_t st)
+{
+    if (a.n <= 0) return cudaSuccess;
+    p3p_init_kernel<<<(a.n + 63) / 64, 64, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pnp(const PnpArgs &a, cudaStream_t st)

@@ -4,10 +4,12 @@
     uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix)        un_pnp_utils.py:6-57
     uncertainty_pnp_v2(points_2d, covars, points_3d, camera_matrix)         un_pnp_utils.py:60-121
     uncertainty_pnp_batch(...)                                              n problems in one launch, CUDA tensors in/out
+    p3p_init_batch(...)                                                     the P3P initial poses for a batch, on the device
 
-The initial pose is still the reference's: OpenCV P3P on the 4 best-weighted points (`cv2.solvePnP(..., SOLVEPNP_P3P)`,
-un_pnp_utils.py:27-31) -- a host-side closed form on 4 points, outside the scope of this layer; pass `init_rt` to skip it
-(for instance the pose of a plain PnP, or of the previous frame).  The refinement runs on the GPU in fp64 with Ceres 2.0's
+The numpy twins keep the reference's initial pose: OpenCV P3P on the 4 best-weighted points (`cv2.solvePnP(..., SOLVEPNP_P3P)`,
+un_pnp_utils.py:27-31) on the host, or an `init_rt` you pass (the pose of a plain PnP, of the previous frame, ...).  The
+batched entry can also take it from `p3p_init_batch` -- the same recipe on the device (csrc/p3p_core.cuh, pinned against
+cv2.solvePnP on the CPU; experimental until its first GPU run).  The refinement runs on the GPU in fp64 with Ceres 2.0's
 default Levenberg-Marquardt options restated (include/pvnet_vote_b200.h); there is no CPU implementation behind it.
 """
 import ctypes
@@ -26,11 +28,12 @@ def _options(max_num_iterations, function_tolerance, gradient_tolerance, paramet
     return o
 
 
-def uncertainty_pnp_batch(points_2d, weights_2d, points_3d, camera_matrix, init_rt, *, max_num_iterations=50,
+def uncertainty_pnp_batch(points_2d, weights_2d, points_3d, camera_matrix, init_rt=None, *, max_num_iterations=50,
                           function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8, return_info=False):
     """points_2d [n,pn,2], weights_2d [n,pn,3] (wxx,wxy,wyy), points_3d [pn,3] or [n,pn,3], camera_matrix [3,3] or [n,3,3],
     init_rt [n,6] (angle-axis, translation): CUDA tensors of any float dtype.  Returns result_rt [n,6] float64 on the same
-    device (and info [n,2] int32 = iterations, termination code when return_info).  Stream-ordered, no host sync."""
+    device (and info [n,2] int32 = iterations, termination code when return_info).  Stream-ordered, no host sync.
+    init_rt=None: the initial poses come from `p3p_init_batch` (the reference's P3P recipe, on the device; experimental)."""
     if not (isinstance(points_2d, torch.Tensor) and points_2d.is_cuda):
         raise RuntimeError("points_2d must be a CUDA tensor")
     dev = points_2d.device
@@ -53,7 +56,7 @@ def uncertainty_pnp_batch(points_2d, weights_2d, points_3d, camera_matrix, init_
     p3 = prep(points_3d, (pn, 3) if shared3 else (n, pn, 3), "points_3d")
     sharedk = camera_matrix.dim() == 2
     km = prep(camera_matrix, (3, 3) if sharedk else (n, 3, 3), "camera_matrix")
-    rt0 = prep(init_rt, (n, 6), "init_rt")
+    rt0 = prep(init_rt, (n, 6), "init_rt") if init_rt is not None else _p3p_init_prepared(p2, p3, w2, km, shared3, sharedk)
     out = torch.empty((n, 6), dtype=torch.float64, device=dev)
     info = torch.zeros((n, 2), dtype=torch.int32, device=dev) if return_info else None
     if n:
@@ -67,6 +70,36 @@ def uncertainty_pnp_batch(points_2d, weights_2d, points_3d, camera_matrix, init_
                 0 if shared3 else pn * 3, 0 if sharedk else 9, ctypes.cast(ctypes.pointer(opt), vp),
                 vp(torch.cuda.current_stream(dev).cuda_stream)))
     return (out, info) if return_info else out
+
+
+def _p3p_init_prepared(p2, p3, w2, km, shared3, sharedk):
+    n, pn = int(p2.shape[0]), int(p2.shape[1])
+    if pn < 4:
+        raise RuntimeError("the P3P initialisation needs at least 4 points per problem")
+    out = torch.empty((n, 6), dtype=torch.float64, device=p2.device)
+    if n:
+        lib = _lib.load()
+        vp = ctypes.c_void_p
+        with torch.cuda.device(p2.device):
+            _lib.check(lib.pvb_uncertainty_pnp_init(
+                vp(p2.data_ptr()), vp(p3.data_ptr()), vp(w2.data_ptr()), vp(km.data_ptr()), vp(out.data_ptr()), n, pn,
+                0 if shared3 else pn * 3, 0 if sharedk else 9, vp(torch.cuda.current_stream(p2.device).cuda_stream)))
+    return out
+
+
+def p3p_init_batch(points_2d, weights_2d, points_3d, camera_matrix):
+    """Initial poses [n,6] as un_pnp_utils.py:25-31 computes them with OpenCV (P3P on the 2nd..4th best-weighted keypoints by
+    wxx+wxy, the best one picks the root), on the device and for the whole batch; NaN rows where no pose is admissible.
+    EXPERIMENTAL in round 1: pinned against cv2.solvePnP on the CPU (tests/test_p3p_host_core.py), first GPU run pending."""
+    if not (isinstance(points_2d, torch.Tensor) and points_2d.is_cuda):
+        raise RuntimeError("points_2d must be a CUDA tensor")
+    dev = points_2d.device
+    n, pn = int(points_2d.shape[0]), int(points_2d.shape[1])
+    f = lambda t: t.to(device=dev, dtype=torch.float64).contiguous()   # noqa: E731
+    shared3, sharedk = points_3d.dim() == 2, camera_matrix.dim() == 2
+    if tuple(weights_2d.shape) != (n, pn, 3) or tuple(points_3d.shape[-2:]) != (pn, 3) or tuple(camera_matrix.shape[-2:]) != (3, 3):
+        raise RuntimeError("shapes: points_2d [n,pn,2], weights_2d [n,pn,3], points_3d [pn,3]|[n,pn,3], camera_matrix [3,3]|[n,3,3]")
+    return _p3p_init_prepared(f(points_2d), f(points_3d), f(weights_2d), f(camera_matrix), shared3, sharedk)
 
 
 def rodrigues(rt):

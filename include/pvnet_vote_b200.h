@@ -182,6 +182,16 @@ PVB_API int pvb_uncertainty_pnp(const double *pts2d, const double *pts3d, const 
                                 const double *init_rt, double *result_rt, int32_t *info, int32_t n, int32_t pn,
                                 int64_t pts3d_stride, int64_t k_stride, const pvb_pnp_options *options, pvb_stream_t stream);
 
+/* Initial poses for pvb_uncertainty_pnp, the reference's recipe on the device (un_pnp_utils.py:25-31:
+ * `idxs = argsort(wxx + wxy)[-4:]`, `cv2.solvePnP(points_3d[idxs], points_2d[idxs], K, ..., flags=cv2.SOLVEPNP_P3P)`): P3P on
+ * the 2nd..4th best-weighted keypoints, the best-weighted one chooses among the (up to four) poses by its reprojection
+ * error.  Same layouts as pvb_uncertainty_pnp; writes init_rt [n,6] (angle-axis, translation); a problem without an
+ * admissible solution gets NaNs (what OpenCV returns there).  pn >= 4.  EXPERIMENTAL in round 1: the arithmetic is pinned
+ * against cv2.solvePnP on the CPU (tests/test_p3p_host_core.py), the device launch had no GPU time yet. */
+PVB_API int pvb_uncertainty_pnp_init(const double *pts2d, const double *pts3d, const double *wgt2d, const double *K,
+                                     double *init_rt, int32_t n, int32_t pn, int64_t pts3d_stride, int64_t k_stride,
+                                     pvb_stream_t stream);
+
 /* Reads the sticky status word of a workspace (synchronises `stream`). */
 PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream_t stream);
 

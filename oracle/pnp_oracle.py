@@ -16,6 +16,10 @@ defaults in include/ceres/solver.h of the vendored headers):
     max_num_iterations 50, function_tolerance 1e-6, gradient_tolerance 1e-10, parameter_tolerance 1e-8,
     initial_trust_region_radius 1e4, max 1e16, min 1e-32, min_relative_decrease 1e-3, min_lm_diagonal 1e-6,
     max_lm_diagonal 1e32, jacobi_scaling on, monotonic steps, max_num_consecutive_invalid_steps 5.
+The constants of the loop can be read in source form in the vendored header-only `include/ceres/tiny_solver.h:171-290`, the same
+authors' compact LM (Jacobi scaling 1/(1+|col|), LM diagonal sqrt(clamp(JtJ_ii, 1e-6, 1e32)/radius), radius /= max(1/3, 1-(2rho-1)^3)
+on acceptance, radius /= v, v *= 2 on rejection); the full minimiser adds min_relative_decrease, the function-tolerance test,
+invalid-step handling and evaluates the gradient test on the unscaled gradient -- restated here from its documentation.
 What IS pinned: the objective (against ceres/rotation.h:563-607 semantics and an independent finite-difference check) and the
 optimum (tests/test_pnp_oracle.py compares with scipy.optimize.least_squares on the same residuals).
 """

@@ -15,6 +15,12 @@
  *   src/ransac_voting.cpp:64  generate_hypothesis_vanishing_pt   pvb_generate_hypothesis_vanishing_point
  *   src/ransac_voting.cpp:85  voting_for_hypothesis_vanishing_pt pvb_voting_for_hypothesis_vanishing_point
  *
+ *   and, for the callers either side of the layer:
+ *   lib/networks/pvnet/resnet18.py:65-76  decode_keypoint         pvb_decode_v3 (+ pvb_estimate_voting_distribution)
+ *   lib/evaluators/linemod/pvnet.py:118-130  weight loop          pvb_uncertainty_weights
+ *   lib/csrc/uncertainty_pnp/src/ext.h  uncertainty_pnp(...)      pvb_uncertainty_pnp (batched)
+ *   un_pnp_utils.py:25-31  cv2.solvePnP(..., SOLVEPNP_P3P)        pvb_uncertainty_pnp_init (experimental)
+ *
  * Conventions
  *   - plain C: device pointers, sizes, strides (in ELEMENTS), a CUDA stream
  *     handle.  No torch types.  All work is enqueued on `stream`; no entry

@@ -84,7 +84,7 @@ def load():
     if _LIB is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python clean-pvnet_b200/build.py` "
+                f"{LIB_PATH} is missing: build it with `python clean_pvnet_b200/build.py` "
                 "(or __graft_entry__.build()). There is no CPU/PyTorch fallback for this op.")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():

@@ -1,6 +1,6 @@
 """Builds libpvnet_vote_b200.so (hand-written sm_100a CUDA behind a C ABI) in-tree with nvcc.
 
-    python clean-pvnet_b200/build.py [--force] [--verbose]
+    python clean_pvnet_b200/build.py [--force] [--verbose]
 
 The .so is git-ignored but travels to the GPU box with the working tree.  No JIT,
 no torch headers: the library's only dependency is the (statically linked) CUDA runtime.

@@ -305,17 +305,38 @@ def ransac_voting_layer_v3_host(mask, vertex, round_hyp_num, inlier_thresh=0.999
 
 
 def install_as_reference_module():
-    """Registers this module under the reference's import path so that
-    `from lib.csrc.ransac_voting.ransac_voting_gpu import ...` (resnet18.py:5) resolves to it,
-    and the pybind twins under `lib.csrc.ransac_voting.ransac_voting`."""
+    """Makes `from lib.csrc.ransac_voting.ransac_voting_gpu import ...` (lib/networks/pvnet/resnet18.py:5) resolve to
+    this module, and `import lib.csrc.ransac_voting.ransac_voting` (ransac_voting_gpu.py:2) to the twins of the pybind
+    extension -- WITHOUT shadowing anything else of the reference tree.
+
+    Only the two leaf modules are replaced.  The parents `lib`, `lib.csrc`, `lib.csrc.ransac_voting` are the REAL
+    packages whenever they can be imported (the normal case: the call sits at the top of run.py / train_net.py with
+    the clean-pvnet checkout on sys.path), so `lib.config`, `lib.networks`, `lib.csrc.nn`, `lib.csrc.uncertainty_pnp`
+    keep importing.  A stand-in package is created only for a parent that does not exist anywhere on sys.path
+    (using this module outside a clean-pvnet checkout).  Idempotent."""
+    import importlib
+    import importlib.util
     this = sys.modules[__name__]
+    parent = None
     for name in ("lib", "lib.csrc", "lib.csrc.ransac_voting"):
-        if name not in sys.modules:
-            m = types.ModuleType(name)
-            m.__path__ = []
-            sys.modules[name] = m
+        mod = sys.modules.get(name)
+        if mod is None:
+            try:
+                found = importlib.util.find_spec(name) is not None
+            except (ImportError, ValueError, AttributeError):
+                found = False
+            if found:
+                mod = importlib.import_module(name)        # the real package; errors inside it propagate
+            else:
+                mod = types.ModuleType(name)
+                mod.__path__ = []                            # genuinely absent: namespace stand-in
+                mod.__pvb_stand_in__ = True
+                sys.modules[name] = mod
+        if parent is not None and not hasattr(parent, name.rsplit(".", 1)[1]):
+            setattr(parent, name.rsplit(".", 1)[1], mod)
+        parent = mod
     sys.modules["lib.csrc.ransac_voting.ransac_voting_gpu"] = this
     sys.modules["lib.csrc.ransac_voting.ransac_voting"] = _ext
-    sys.modules["lib.csrc.ransac_voting"].ransac_voting_gpu = this
-    sys.modules["lib.csrc.ransac_voting"].ransac_voting = _ext
+    parent.ransac_voting_gpu = this
+    parent.ransac_voting = _ext
     return this

@@ -2,7 +2,7 @@
 """Build the UNMODIFIED reference `ransac_voting` CUDA extension into oracle/_ref/.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under `oracle/` is imported by the product
-package (`clean-pvnet_b200/`); only tests/, __graft_entry__.smoke() and
+package (`clean_pvnet_b200/`); only tests/, __graft_entry__.smoke() and
 bench.py (reference arm / cpu_baseline leg) may touch it.
 
 What this does (all outputs land in oracle/_ref/, which is git-ignored but

@@ -2,7 +2,7 @@
  * pvnet_oracle.c -- CPU restatement of clean-pvnet's RANSAC voting layer.
  *
  * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA
- * product in clean-pvnet_b200/csrc.  Only tests/, __graft_entry__.smoke()
+ * product in clean_pvnet_b200/csrc.  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / reference legs may build, load or call it.
  * The product never links or imports anything under oracle/.
  *
@@ -62,7 +62,7 @@ ORC_API void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uin
 }
 
 /* Counter layout of the philox sampling mode (mirrored, independently, in
- * clean-pvnet_b200/csrc/philox.cuh).  tag: 1 = v3 pair indices, 2 = v3
+ * clean_pvnet_b200/csrc/philox.cuh).  tag: 1 = v3 pair indices, 2 = v3
  * thinning, 3 = distribution pair indices, 4 = distribution thinning. */
 enum { ORC_TAG_V3_IDX = 1, ORC_TAG_V3_SEL = 2, ORC_TAG_DIST_IDX = 3, ORC_TAG_DIST_SEL = 4 };
 

@@ -1,6 +1,6 @@
-// Host build of clean-pvnet_b200/csrc/p3p_core.cuh for the CPU test-suite (tests/test_p3p_host_core.py).
+// Host build of clean_pvnet_b200/csrc/p3p_core.cuh for the CPU test-suite (tests/test_p3p_host_core.py).
 // Test infrastructure only -- nothing in the product links or loads this.
-#include "../clean-pvnet_b200/csrc/p3p_core.cuh"
+#include "../clean_pvnet_b200/csrc/p3p_core.cuh"
 
 extern "C" int p3p_host_solve4(const double *pts3d /*[4][3]*/, const double *pts2d /*[4][2]*/, const double *K /*[3][3]*/,
                                double *rt /*[6]*/)

@@ -1,7 +1,7 @@
-// Host build of clean-pvnet_b200/csrc/pnp_core.cuh for the CPU test-suite (tests/test_pnp_host_core.py): the same
+// Host build of clean_pvnet_b200/csrc/pnp_core.cuh for the CPU test-suite (tests/test_pnp_host_core.py): the same
 // arithmetic and trust-region state machine the CUDA kernel runs, driven by a serial loop over the points instead of the
 // warp reduction.  Test infrastructure only -- nothing in the product links or loads this.
-#include "../clean-pvnet_b200/csrc/pnp_core.cuh"
+#include "../clean_pvnet_b200/csrc/pnp_core.cuh"
 
 static void normal_at(const double *pose, const double *pts2d, const double *pts3d, const double *wgt2d, const double *cam,
                       int pn, pvb::PnpNormal &n)

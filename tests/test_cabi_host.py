@@ -134,7 +134,7 @@ def test_install_as_reference_module(pvb):
 
 
 def test_product_does_not_import_the_oracle():
-    pkg = os.path.join(ROOT, "clean-pvnet_b200")
+    pkg = os.path.join(ROOT, "clean_pvnet_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

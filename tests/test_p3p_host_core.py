@@ -1,4 +1,4 @@
-"""CPU: the closed-form initial pose of the uncertainty PnP (clean-pvnet_b200/csrc/p3p_core.cuh, compiled as host code by
+"""CPU: the closed-form initial pose of the uncertainty PnP (clean_pvnet_b200/csrc/p3p_core.cuh, compiled as host code by
 tests/p3p_host_harness.cpp) against the reference's own initialiser, `cv2.solvePnP(..., flags=cv2.SOLVEPNP_P3P)` called exactly
 as un_pnp_utils.py:25-31 calls it.  OpenCV runs here, so this pin is against the real thing, not a restatement."""
 import ctypes

@@ -1,4 +1,4 @@
-"""CPU: the arithmetic core of the CUDA uncertainty-PnP kernel (clean-pvnet_b200/csrc/pnp_core.cuh), compiled as host code
+"""CPU: the arithmetic core of the CUDA uncertainty-PnP kernel (clean_pvnet_b200/csrc/pnp_core.cuh), compiled as host code
 by tests/pnp_host_harness.cpp, against the oracle.  The kernel (csrc/pnp.cu) adds only the warp reduction of the normal
 equations around this core, so residuals, Jacobians, the 6x6 solve and every branch of the trust-region state machine are
 checked here without a GPU; tests/test_gpu_pnp.py then checks the kernel itself."""

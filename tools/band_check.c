@@ -1,6 +1,6 @@
 /* band_check.c -- empirical check of the vote kernel's guard band (DESIGN.md "Guard band").
  *
- * Re-states, for the host, the fast cone test of clean-pvnet_b200/csrc/vote.cu (same IEEE operation
+ * Re-states, for the host, the fast cone test of clean_pvnet_b200/csrc/vote.cu (same IEEE operation
  * sequence: fmaf / fp32 mul,add,div,sqrt; build with -ffp-contract=off) next to the reference predicate
  * (oracle vote_one == ransac_voting_kernel.cu:107-125) and searches, with samples concentrated on the
  * cone boundary, for tests where the two disagree.  For every disagreement it records

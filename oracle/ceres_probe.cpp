@@ -27,10 +27,14 @@ struct TraceCallback : public ceres::IterationCallback {
 };
 }
 
+static char g_last_message[512] = "";
+
 extern "C" {
 
+const char *ceres_probe_last_message(void) { return g_last_message; }
+
 // summary8 = {termination_type, #IterationSummary, initial_cost, final_cost, successful, unsuccessful steps,
-//             linear_solver_type_used, 0};  trace = [rows][8] as in TraceCallback; returns the number of rows written.
+//             linear_solver_type_used, stop reason (codes below)};  trace = [rows][8] as in TraceCallback; returns the number of rows written.
 int ceres_probe(double *pts2d, double *pts3d, double *wgt2d, double *K, double *init_rt, double *result_rt, int pn,
                 double *summary8, double *trace, int max_rows)
 {
@@ -57,7 +61,17 @@ int ceres_probe(double *pts2d, double *pts3d, double *wgt2d, double *K, double *
     summary8[4] = (double)summary.num_successful_steps;
     summary8[5] = (double)summary.num_unsuccessful_steps;
     summary8[6] = (double)summary.linear_solver_type_used;
-    summary8[7] = 0.0;
+    // why it stopped, from Summary::message (trust_region_minimizer.cc): 1 gradient, 2 parameter, 3 function tolerance,
+    // 4 trust-region radius, 5 iteration cap, 6 anything else (failure / invalid steps), same codes as pvb_uncertainty_pnp's info
+    const std::string &m = summary.message;
+    double why = 6.0;
+    if (m.find("Gradient tolerance reached") != std::string::npos) why = 1.0;
+    else if (m.find("Parameter tolerance reached") != std::string::npos) why = 2.0;
+    else if (m.find("Function tolerance reached") != std::string::npos) why = 3.0;
+    else if (m.find("trust region radius") != std::string::npos || m.find("Trust region radius") != std::string::npos) why = 4.0;
+    else if (m.find("Maximum number of iterations reached") != std::string::npos) why = 5.0;
+    summary8[7] = why;
+    strncpy(g_last_message, m.c_str(), sizeof(g_last_message) - 1);
     int n = (int)(rows.size() / 8);
     if (n > max_rows) n = max_rows;
     if (n > 0) memcpy(trace, rows.data(), sizeof(double) * 8 * (size_t)n);

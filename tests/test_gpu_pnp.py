@@ -143,3 +143,36 @@ def test_input_checks(pvb):
     with pytest.raises(RuntimeError):
         pvb.uncertainty_pnp_batch(uv, torch.zeros((2, 9, 2), device="cuda"), torch.zeros((9, 3), device="cuda"),
                                   torch.zeros((3, 3), device="cuda"), torch.zeros((2, 6), device="cuda"))
+
+
+def test_kernel_follows_real_ceres(pvb):
+    """pvb_uncertainty_pnp against tests/golden/ceres_pnp.npz: 284 problems solved by the reference's own Ceres 2.0 binary
+    through its unmodified uncertainty_pnp.cpp (tests/golden/make_golden_ceres.py; CPU counterpart tests/test_ceres_golden.py).
+    Same stop reason, same iteration count and the same pose to 1e-9 on the problems an independent implementation can follow
+    (`stable`: the result moves < 1e-10 under a 1e-13 perturbation of the start) -- the warp's butterfly sums differ from
+    Eigen's in the last bits, which may flip a convergence test on a few of them: then the slack of Ceres' own
+    function_tolerance applies (2e-4), for at most 3 %."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ceres_pnp.npz"))
+    same = total = 0
+    for pn in np.unique(G["pn"]):
+        idx = np.nonzero(G["pn"] == pn)[0]
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()   # noqa: E731
+        rt, info = pvb.uncertainty_pnp_batch(t(G["pts2d"][idx, :pn]), t(G["wgt2d"][idx, :pn]), t(G["pts3d"][idx, :pn]),
+                                             t(G["K"][idx]), t(G["init_rt"][idx]), return_info=True)
+        rt, info = rt.cpu().numpy(), info.cpu().numpy()
+        for j, i in enumerate(idx):
+            if G["kind"][i] == "optimum":
+                assert np.abs(rt[j] - G["result_rt"][i]).max() < 1e-8, i
+                continue
+            if not G["stable"][i]:
+                assert 1 <= info[j, 1] <= 6, i
+                continue
+            total += 1
+            want_it = int(G["iteration_summaries"][i]) - (0 if G["reason"][i] in (2, 3) else 1)
+            if (info[j, 0], info[j, 1]) == (want_it, G["reason"][i]):
+                same += 1
+                assert np.abs(rt[j] - G["result_rt"][i]).max() < 1e-9, i
+            else:
+                assert np.abs(rt[j] - G["result_rt"][i]).max() < 2e-4, i
+    assert total >= 230 and same >= 0.97 * total, (same, total)

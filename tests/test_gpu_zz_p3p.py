@@ -1,17 +1,14 @@
 """GPU: the device launch of the P3P initialisation (pvb_uncertainty_pnp_init, csrc/pnp.cu p3p_init_kernel).
 
-Sorted last on purpose and marked xfail(strict=False): the kernel was written after round 1's GPU budget was spent, so its
-first run on a GPU is the driver's end-of-round run.  Its arithmetic (csrc/p3p_core.cuh) is pinned against cv2.solvePnP on
-the CPU by tests/test_p3p_host_core.py; what is new here is only the launch, the point selection on the device and the memory
-layout.  An XPASS in the report means the device path works and the marker can go."""
+Its arithmetic (csrc/p3p_core.cuh) is pinned against cv2.solvePnP on the CPU by tests/test_p3p_host_core.py; what is checked
+here is the launch, the point selection on the device and the memory layout (first GPU run: the round-1 driver, passed)."""
 import numpy as np
 import pytest
 import torch
 
 from util import pnp_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run of the P3P launch (written after the round's GPU budget)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_device_p3p_matches_opencv(pvb):

@@ -6,8 +6,10 @@
 
 One "step" = one ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99) call over one batch of
 BASELINE.json's configs[1] ("cfg2": B=16, 480x640, K=9, 512 hypotheses, ~30 % mask fill, int64 mask,
-contiguous [B,H,W,K,2] vertex) per GPU; weak scaling (every rank owns a full batch, results
-all_gathered over NCCL inside the step).  Prints ONE JSON line on rank 0.
+contiguous [B,H,W,K,2] vertex) per GPU; weak scaling (every rank owns a full batch; every rank's keypoints
+reach every rank inside the step: the refit kernel stores them into the peers' HBM over NVLink, see
+clean_pvnet_b200/parallel.py).  `--workload cfg4` runs BASELINE.json's configs[3] instead (B=128, 720x540, K=17,
+sharded over the ranks: strong scaling).  Prints ONE JSON line on rank 0.
 
   value      whole-job images*keypoints/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the host-buffer entry (pinned host inputs -> H2D -> kernels -> D2H)
@@ -36,12 +38,16 @@ UNIT = "images*keypoints/s"
 WORKLOAD = "cfg2"
 HN = 512
 THRESH = 0.99
-KERNELS_PER_STEP = 6   # mask_bits, thin_scan, gather, generate, vote, refit
+KERNELS_PER_STEP = 6   # mask_bits, thin_scan, gather, generate, vote, refit (+1 exchange_wait per step when N > 1)
+
+
+def workload_string(name, cfg, layout, per_gpu_images):
+    """The SAME string in both arms (ours / --impl reference): what one GPU processes per step."""
+    return (f"{name}: B={per_gpu_images} images per GPU per step, {cfg['H']}x{cfg['W']}, K={cfg['K']}, hn={HN}, "
+            f"inlier_thresh={THRESH}, fill~30%, int64 mask, vertex layout={layout}, max_num=30000")
 # dram__bytes_read.sum + dram__bytes_write.sum of one vote_kernel launch on this workload, from the committed
 # `ncu --set full` capture (profiles/r01_ncu_summary.txt): 39 394 304 + 256 bytes
 VOTE_KERNEL_DRAM_BYTES = 39394560
-# the opt-in tensor-path experiment (PVB_VOTE_VARIANT=4|5; not the shipped default): 39 408 640 + 3 072 bytes
-VOTE_MMA_KERNEL_DRAM_BYTES = 39411712
 
 
 def _env_int(name, default):
@@ -193,7 +199,6 @@ def run_ours(args):
     from clean_pvnet_b200 import _lib, parallel, synth
 
     rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
-    tensor_path = _env_int("PVB_VOTE_VARIANT", 0) >= 4     # opt-in experiment (tooling); the shipped default is 0
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -201,30 +206,42 @@ def run_ours(args):
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
-    cfg = synth.CONFIGS[WORKLOAD]
-    B, H, W, K = cfg["B"], cfg["H"], cfg["W"], cfg["K"]
-    mask, vertex, _ = synth.make_inputs(WORKLOAD, device=dev, seed=1234 + 2 + rank, layout=args.layout)
-    total = B * world
-
+    wl = args.workload
+    cfg = synth.CONFIGS[wl]
+    H, W, K = cfg["H"], cfg["W"], cfg["K"]
+    if wl == "cfg2":                       # weak scaling: a full cfg-2 batch on every rank
+        B = cfg["B"]
+        total = B * world
+        scaling = "weak"
+    else:                                  # cfg-4: the named batch sharded over the ranks
+        total = cfg["B"]
+        lo_, hi_ = parallel.shard_bounds(total, world, rank)
+        B = hi_ - lo_
+        scaling = "strong"
+        if total % world:
+            raise SystemExit(f"{wl}: {total} images do not split evenly over {world} ranks")
+    mask, vertex, _ = synth.make_inputs(wl, device=dev, seed=1234 + 2 + rank, layout=args.layout, B=B)
+    layer = None
+    if world > 1:
+        layer = parallel.ShardedVotingLayer(total, K, depth=4, gather=args.gather, device=dev)
     pending = []
 
     def step(i):
-        local_out = pvb.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH, seed=1000 + i,
-                                               img_base=rank * B)
-        if world > 1:
-            # the keypoint all_gather (4.6 KB per rank) runs on NCCL's stream and overlaps the next step's
-            # kernels; every gather is waited for inside the timed region (drain() below)
-            finish, work = parallel.all_gather_ragged(local_out, total, async_op=True)
-            pending.append((finish, work))
-            return finish
-        return lambda: local_out
+        if layer is not None:
+            # the refit kernel pushes this rank's [B,K,2] into every peer's ring (NVLink stores); the wait of step i-4
+            # is enqueued by the layer before step i; everything still pending is waited for inside the timed region (drain)
+            p = layer(mask, vertex, HN, inlier_thresh=THRESH, seed=1000 + i)
+            pending.append(p)
+            return p
+        return pvb.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH, seed=1000 + i, img_base=rank * B)
 
     def drain():
         res = None
-        for finish, work in pending:
-            work.wait()
-            res = finish()
-        pending.clear()
+        if layer is not None:
+            layer.drain()
+            if pending:
+                res = pending[-1].result()
+            pending.clear()
         return res
 
     # one debug call for the workload's tn (units of algorithmic bytes / tests)
@@ -244,15 +261,32 @@ def run_ours(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    last = None
     for i in range(args.steps):
-        out_fn = step(i)
+        last = step(i)
     gathered = drain()
     ev1.record()
     torch.cuda.synchronize()
-    out = gathered if gathered is not None else out_fn()
+    out = gathered if gathered is not None else last
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
+    # ---- outside the timed region: the gathered result is what N single-GPU calls produce
+    gather_check = None
+    if layer is not None:
+        layer.check()                                    # raises if any exchange wait timed out
+        mine = last.local                                # this rank's own result of the last step
+        lo_g = rank * B
+        ok = bool(torch.equal(out[lo_g:lo_g + B], mine))
+        every = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(every, out.contiguous())         # NCCL, check only
+        ok = ok and all(bool(torch.equal(e, out)) for e in every)
+        # and equal to a plain single-GPU call on this rank's shard with the same seed / global image index
+        again = pvb.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH, seed=1000 + args.steps - 1, img_base=lo_g)
+        ok = ok and bool(torch.equal(again, mine))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_check = "ok" if int(flag.item()) == 1 else "MISMATCH"
     ms = ev0.elapsed_time(ev1)
     import ctypes
     stage = (ctypes.c_double * 4)()
@@ -269,6 +303,9 @@ def run_ours(args):
     # ---- extras (context, not the headline): the un_pnp production pair (resnet18.py:71-72) and B=1 latency
     extras = {}
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
+
         def timed(fn, n):
             for _ in range(3):
                 fn()
@@ -283,6 +320,8 @@ def run_ours(args):
         mean = out[rank * B:(rank + 1) * B] if world > 1 else out
         extras["estimate_voting_distribution_ms"] = timed(
             lambda: pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, seed=7, img_base=rank * B), 10)
+        extras["v3_plain_call_ms"] = timed(
+            lambda: pvb.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH, seed=7, img_base=rank * B), 30)
         extras["v3_latency_b1_ms"] = timed(
             lambda: pvb.ransac_voting_layer_v3(mask[:1], vertex[:1], HN, inlier_thresh=THRESH, seed=7), 50)
         # decode_keypoint's argmax fused into the select kernel (pvb_decode_v3) vs torch.argmax + v3
@@ -296,6 +335,8 @@ def run_ours(args):
     except Exception as e:
         extras["error"] = str(e)
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         # SURVEY 8f rows 2+3: the un_pnp tail for this batch -- cov -> inv(sqrtm(cov)) weights, then the batched LM pose
         # refinement (one warp per image), from the keypoints / covariances the voting layer just produced
         kp2d, var = pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, seed=7, img_base=rank * B)
@@ -310,12 +351,12 @@ def run_ours(args):
     # ---- end-to-end: pinned host inputs -> H2D -> kernels -> D2H, through the public host entry
     mh, vh = mask.cpu().pin_memory(), vertex.contiguous().cpu().pin_memory()
     oh = torch.empty((B, K, 2), dtype=torch.float32).pin_memory()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 20)) if not args.quick else 1
 
-    def e2e_run(zero_copy):
+    def e2e_run(mode):
         for i in range(3):
             pvb.ransac_voting_layer_v3_host(mh, vh, HN, inlier_thresh=THRESH, seed=1, img_base=rank * B,
-                                            chunk_images=args.chunk, out=oh, device=dev, zero_copy=zero_copy)
+                                            chunk_images=args.chunk, out=oh, device=dev, mode=mode)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -323,7 +364,7 @@ def run_ours(args):
         e0.record()
         for i in range(e2e_steps):
             pvb.ransac_voting_layer_v3_host(mh, vh, HN, inlier_thresh=THRESH, seed=1000 + i, img_base=rank * B,
-                                            chunk_images=args.chunk, out=oh, device=dev, zero_copy=zero_copy)
+                                            chunk_images=args.chunk, out=oh, device=dev, mode=mode)
         e1.record()
         torch.cuda.synchronize()
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -331,10 +372,11 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         return float(te.item()) / e2e_steps
 
-    e2e_staged_ms = e2e_run(False)      # both tensors copied host->device (393 MB per step and GPU)
-    e2e_ms = e2e_run(True)              # kernels read the pinned tensors in place over PCIe
+    e2e_staged_ms = e2e_run("staged")     # both tensors copied host->device (393 MB per step and GPU at cfg-2)
+    e2e_inplace_ms = e2e_run("inplace")   # both tensors read in place by the kernels (round 1's mode)
+    e2e_ms = e2e_run("auto")              # mask by DMA, selected vertex rows read in place
     staged_bytes = mh.numel() * mh.element_size() + vh.numel() * vh.element_size()
-    # bytes that cross the bus in zero-copy mode: the whole mask + K float2 per SELECTED pixel
+    # bytes that cross the bus in the default mode: the whole mask (DMA) + K float2 per SELECTED pixel (in-place reads)
     h2d = mh.numel() * mh.element_size() + tn_sum * K * 8
     d2h = oh.numel() * oh.element_size()
 
@@ -348,32 +390,40 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{WORKLOAD}: B={B}/GPU 480x640 K={K} hn={HN} inlier_thresh={THRESH} fill~30% "
-                            f"{str(mask.dtype).replace('torch.', '')} mask, vertex layout={args.layout}, max_num=30000",
+                "workload": workload_string(wl, cfg, args.layout, B),
                 "global_batch": total, "selected_pixels_per_image": tn_sum / B,
                 "l2": "inputs larger than L2 (mask+vertex = %.0f MB per GPU > 126 MB); no explicit flush" % (staged_bytes / 1e6),
-                "parallelism": f"dp{world} (images sharded; NCCL all_gather of [B,K,2] per step, asynchronous on NCCL's "
-                               f"stream, all waited for inside the timed region)" if world > 1 else "single GPU",
+                "parallelism": (f"dp{world} (images sharded; gather={layer.mode}: "
+                                + ("every rank's [B,K,2] stored into all peers' HBM over NVLink by the refit kernel, flag-"
+                                   "synchronised, no collective in the steady state; all waits inside the timed region)"
+                                   if layer.mode == "peer" else
+                                   "one torch.distributed all_gather per step, all waited for inside the timed region)"))
+                               if world > 1 else "single GPU",
                 "sampling": "philox (in-kernel), new seed every step",
             },
             "clocks": clocks,
             "e2e": {"value": total * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "chunk_images": args.chunk,
-                    "api": "ransac_voting_layer_v3_host -> pvb_ransac_voting_v3_host (pinned host buffers, zero-copy: "
-                           "mask streamed once, only the selected pixels' vertex rows fetched over PCIe)",
+                    "api": "ransac_voting_layer_v3_host -> pvb_ransac_voting_v3_host (pinned host buffers; mask by DMA, "
+                           "only the selected pixels' vertex rows fetched in place over PCIe)",
+                    "pcie_gb_s": h2d / (e2e_ms * 1e-3) / 1e9,
+                    "inplace": {"value": total * K / (e2e_inplace_ms * 1e-3), "ms_per_step": e2e_inplace_ms,
+                                "h2d_bytes_per_step": h2d,
+                                "note": "same entry, mode='inplace': mask and vertex rows both read in place (round 1's mode)"},
                     "staged": {"value": total * K / (e2e_staged_ms * 1e-3), "ms_per_step": e2e_staged_ms,
                                "h2d_bytes_per_step": staged_bytes,
-                               "note": "same entry with zero_copy=False: both tensors copied with cudaMemcpyAsync"}},
-            "gpu_launches": KERNELS_PER_STEP * args.steps,
+                               "note": "same entry, mode='staged': both tensors copied with cudaMemcpyAsync"}},
+            "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 and layer.mode == "peer" else 0)) * args.steps,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None,
-                "traffic": args.traffic if args.traffic is not None else
-                (VOTE_MMA_KERNEL_DRAM_BYTES if tensor_path else VOTE_KERNEL_DRAM_BYTES),
-                "kernel": "pvb::vote_mma_kernel<8,8,2,1024> (opt-in experiment)" if tensor_path else "pvb::vote_kernel<4,128,8,512,4>",
+                "traffic": args.traffic if args.traffic is not None else (VOTE_KERNEL_DRAM_BYTES if wl == "cfg2" else None),
+                "traffic_source": "constant from the committed `ncu --set full` capture of this kernel on this workload "
+                                  "(profiles/r01_ncu_summary.txt); not re-measured per run",
+                "kernel": "pvb::vote_kernel<4,128,8,512,4>",
                 "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
                 "peak_source": peak_src,
                 "note": "the vote kernel is FP32-issue bound by construction (hn inlier tests per 16 loaded bytes); "
@@ -381,16 +431,17 @@ def run_ours(args):
             },
             "alu": {"inlier_tests_per_step": tests, "tests_per_s_vote_kernel": tests / (vote_ms * 1e-3) if vote_ms else None,
                     "lane_ops_peak_per_s": 148 * 128 * sm_mhz * 1e6,
-                    "sass_instr_per_test": 3.4 if tensor_path else 7.1,
-                    "note": ("opt-in tensor-path experiment: 217 SASS instr per warp per 2 x (16 pixels x 64 hypotheses) = 32 "
-                             "HMMA.1688.F32.TF32 (tf32x3 split) + 64 FADD + 64 LEA.HI + 32 FMNMX3 + 4 LDS.128; HMMA issues "
-                             "every 8 cycles per SMSP (tools/microbench3.cu)") if tensor_path else
-                            ("454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
+                    "sass_instr_per_test": 7.1,
+                    "note": ("454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
                              "24 LDS); tools/microbench.cu bounds this mix at 610 cycles/block/SMSP => ~4.2 T tests/s")},
             "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
             "extras": extras,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if gather_check is not None:
+            line["gather_check"] = gather_check
+            if layer.gather_error:
+                line["gather_fallback_reason"] = layer.gather_error
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             try:
                 line["cpu_baseline"] = _cpu_baseline(mask, vertex, K, args.cpu_seconds)
             except Exception as e:   # the oracle is a checker; its absence must not hide the GPU number
@@ -399,6 +450,7 @@ def run_ours(args):
         sys.stdout.flush()
     if world > 1:
         dist.barrier()
+        layer.close()
         dist.destroy_process_group()
 
 
@@ -408,8 +460,11 @@ def run_reference(args):
         return          # the reference has no multi-GPU path: rank 0 alone runs it
     import torch
     from clean_pvnet_b200 import synth
-    cfg = synth.CONFIGS[WORKLOAD]
-    B, H, W, K = cfg["B"], cfg["H"], cfg["W"], cfg["K"]
+    wl = args.workload
+    cfg = synth.CONFIGS[wl]
+    H, W, K = cfg["H"], cfg["W"], cfg["K"]
+    world = _env_int("WORLD_SIZE", 1)
+    B = cfg["B"] if wl == "cfg2" else cfg["B"] // world     # what ONE GPU of our arm processes per step
     local = _env_int("LOCAL_RANK", 0)
     gpu_ref = None
     if torch.cuda.is_available():
@@ -425,7 +480,7 @@ def run_reference(args):
     if gpu_ref is not None:
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
-        mask, vertex, _ = synth.make_inputs(WORKLOAD, device=dev, seed=1234 + 2, layout=args.layout)
+        mask, vertex, _ = synth.make_inputs(wl, device=dev, seed=1234 + 2, layout=args.layout, B=B)
         for i in range(max(args.warmup, 3)):
             torch.manual_seed(i)
             gpu_ref.ransac_voting_layer_v3(mask, vertex, HN, inlier_thresh=THRESH)
@@ -462,21 +517,21 @@ def run_reference(args):
         except Exception as e:
             extras["error"] = str(e)
         line = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, extras=extras,
-                    config={"workload": f"{WORKLOAD}: B={B} 480x640 K={K} hn={HN} inlier_thresh={THRESH} fill~30% int64 mask, "
-                                        f"vertex layout={args.layout}, max_num=30000",
+                    config={"workload": workload_string(wl, cfg, args.layout, B),
                             "global_batch": B, "parallelism": "single GPU (the reference has no multi-GPU path)",
                             "implementation": "unmodified clean-pvnet lib/csrc/ransac_voting (CUDA ext compiled for sm_100 "
                                               "by oracle/build_ref.py) through its own ransac_voting_layer_v3"},
                     cpu_baseline={"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
-                                  "sample": f"{args.steps} full {WORKLOAD} batches on 1 GPU (the reference path is CUDA-only, "
+                                  "sample": f"{args.steps} batches of {B} {wl} images on 1 GPU (the reference path is CUDA-only, "
                                             "ransac_voting.cpp:7-9)"},
                     e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     else:
-        mask, vertex, _ = synth.make_inputs(WORKLOAD, device="cpu", seed=1234 + 2, B=min(B, 4))
+        mask, vertex, _ = synth.make_inputs(wl, device="cpu", seed=1234 + 2, B=min(B, 4))
         cb = _cpu_baseline(mask, vertex, K, args.cpu_seconds)
         line = dict(base, value=cb["value"], ms_per_step=None,
-                    config={"workload": f"{WORKLOAD} (bounded sample) through the CPU oracle port; reference CUDA "
-                                        "extension not loadable here"},
+                    config={"workload": workload_string(wl, cfg, args.layout, B),
+                            "implementation": "bounded sample through the CPU oracle port; the reference CUDA extension "
+                                              "is not loadable here"},
                     cpu_baseline=cb, e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                                           "d2h_bytes_per_step": 0})
     print(json.dumps(line))
@@ -490,9 +545,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="interleaved", choices=["interleaved", "planar"])
+    ap.add_argument("--workload", default=WORKLOAD, choices=["cfg2", "cfg4"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "collective"],
+                    help="N>1: how every rank's keypoints reach every rank (clean_pvnet_b200/parallel.py)")
     ap.add_argument("--chunk", type=int, default=2, help="images per H2D chunk of the end-to-end path")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling passes (ncu): timed steps only -- no extras, no end-to-end runs, no CPU baseline")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes/launch of the vote kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

@@ -9,7 +9,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpvnet_vote_b200.so")
 
-PVB_OK, PVB_ERR_INVALID, PVB_ERR_CUDA, PVB_ERR_WORKSPACE, PVB_ERR_CAPACITY = range(5)
+PVB_OK, PVB_ERR_INVALID, PVB_ERR_CUDA, PVB_ERR_WORKSPACE, PVB_ERR_CAPACITY, PVB_ERR_TIMEOUT = range(6)
+PVB_HOST_STAGE_VERTEX, PVB_HOST_INPLACE_MASK = 2, 4
+PVB_IPC_HANDLE_BYTES = 64
 (PVB_MASK_U8, PVB_MASK_I8, PVB_MASK_I16, PVB_MASK_I32, PVB_MASK_I64, PVB_MASK_F32, PVB_MASK_F64) = range(7)
 PVB_SELECT_BYTE, PVB_SELECT_EQ1 = 0, 1
 
@@ -32,7 +34,7 @@ class PvbDesc(ctypes.Structure):
 class PvbLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in
                 ("total", "status", "fgsum", "nz", "tn", "state", "bits", "wordoff", "blocktot", "xy", "dirs", "hyp",
-                 "counts", "win", "refit_partial", "refit_ticket")] + [
+                 "counts", "win", "refit_partial", "refit_ticket", "refit_done")] + [
                     ("nwords", ctypes.c_int32), ("nblocks", ctypes.c_int32), ("capacity", ctypes.c_int32),
                     ("refit_splits", ctypes.c_int32)]
 
@@ -61,8 +63,17 @@ SIGNATURES = {
     "pvb_uncertainty_pnp_init": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_int64, ctypes.c_int64, _vp]),
     "pvb_read_status": (ctypes.c_int, [_dp, _vp, _vp]),
     "pvb_host_scratch_bytes": (_sz, [_dp, _i32]),
-    "pvb_ransac_voting_v3_host": (ctypes.c_int, [_dp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
-    "pvb_set_host_mode": (ctypes.c_int, [_i32]),
+    "pvb_ransac_voting_v3_host": (ctypes.c_int, [_dp, _vp, _vp, _vp, _i32, ctypes.c_uint32, _vp, _sz, _vp]),
+    "pvb_exchange_create": (ctypes.c_int, [_i32, _i32, _i32, _sz, ctypes.POINTER(ctypes.c_void_p)]),
+    "pvb_exchange_bytes_per_rank": (_sz, [_vp]),
+    "pvb_exchange_base": (ctypes.c_void_p, [_vp]),
+    "pvb_exchange_get_handle": (ctypes.c_int, [_vp, _vp]),
+    "pvb_exchange_connect": (ctypes.c_int, [_vp, _vp]),
+    "pvb_exchange_connect_ptrs": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "pvb_ransac_voting_v3_push": (ctypes.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, ctypes.c_uint64, _vp]),
+    "pvb_exchange_wait": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, ctypes.c_double, _vp]),
+    "pvb_exchange_status": (ctypes.c_int, [_vp, _vp]),
+    "pvb_exchange_destroy": (ctypes.c_int, [_vp]),
     "pvb_profile_enable": (ctypes.c_int, [_i32]),
     "pvb_profile_reset": (ctypes.c_int, []),
     "pvb_set_tuning": (ctypes.c_int, [_i32, _i32]),

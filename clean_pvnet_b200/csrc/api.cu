@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <new>
 #include <vector>
 #include "kernels.h"
 
@@ -34,7 +36,6 @@ struct ProfCall {
     bool head;                                                   // first piece of an API call
 };
 thread_local bool g_prof_on = false;
-bool g_host_zero_copy = true;      // pvb_set_host_mode(): read pinned host inputs in place over PCIe
 thread_local std::vector<ProfCall> g_prof_calls;
 thread_local std::vector<cudaEvent_t> g_prof_pool;
 
@@ -105,6 +106,7 @@ int make_layout(const pvb_desc *d, pvb_layout *L)
     L->tn = take(B * sizeof(int));
     L->state = take(B * sizeof(int));
     L->refit_ticket = take(B * K * sizeof(int));
+    L->refit_done = take(sizeof(int));
     L->bits = take(B * nwords * sizeof(uint32_t));
     L->wordoff = take(B * nwords * sizeof(int));
     L->blocktot = take(B * nblocks * sizeof(int));
@@ -128,6 +130,7 @@ struct Plan {
     VoteArgs v;
     float2 *win;
     RefitScratch refit;
+    int *done;            // results written by the refit kernel (exchange tail)
 };
 
 int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
@@ -174,12 +177,13 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     P->refit.partial = reinterpret_cast<double *>(w + L.refit_partial);
     P->refit.ticket = reinterpret_cast<int *>(w + L.refit_ticket);
     P->refit.splits = L.refit_splits;
+    P->done = reinterpret_cast<int *>(w + L.refit_done);
     return PVB_OK;
 }
 
 int run_select(const Plan &P, cudaStream_t st)
 {
-    // status, fgsum, nz, tn, state, refit tickets: contiguous at the start of the workspace
+    // status, fgsum, nz, tn, state, refit tickets, refit_done: contiguous at the start of the workspace
     cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.bits, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(header)");
     e = launch_select(P.s, st);
@@ -201,6 +205,40 @@ int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
     e = launch_vote(P.v, st);
     if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
     prof_end(pc, PVB_STAGE_VOTE, st);
+    return PVB_OK;
+}
+
+// ---- multi-GPU exchange object (exchange.cu holds the kernels and the design notes) ------------------------------
+} // namespace
+
+struct pvb_exchange {
+    int rank, world, slots, device;
+    size_t bytes_per_rank;      // 16-byte multiple
+    size_t flags_off, status_off, total;
+    char *local;                // this rank's ring (cudaMalloc)
+    char *peer[PVB_MAX_PEERS];  // every rank's ring as seen from this device (peer[rank] == local)
+    bool ipc_opened[PVB_MAX_PEERS];
+    bool connected;
+};
+
+namespace {
+
+int exchange_push_args(pvb_exchange *ex, uint64_t seq, size_t nbytes, int *done, PeerPush *pp)
+{
+    memset(pp, 0, sizeof(*pp));
+    if (!ex) return PVB_OK;
+    if (!ex->connected) return fail(PVB_ERR_INVALID, "exchange is not connected (pvb_exchange_connect*)");
+    if (seq == 0) return fail(PVB_ERR_INVALID, "seq must be >= 1");
+    if (nbytes > ex->bytes_per_rank) return fail(PVB_ERR_INVALID, "result block (%zu bytes) exceeds the exchange's bytes_per_rank (%zu)", nbytes, ex->bytes_per_rank);
+    const size_t slot = (size_t)((seq - 1) % (uint64_t)ex->slots);
+    pp->world = ex->world;
+    pp->nfloats = (int)(nbytes / sizeof(float));
+    pp->seq = seq;
+    pp->done = done;
+    for (int r = 0; r < ex->world; ++r) {
+        pp->recv[r] = reinterpret_cast<float *>(ex->peer[r] + (slot * ex->world + ex->rank) * ex->bytes_per_rank);
+        pp->flag[r] = reinterpret_cast<unsigned long long *>(ex->peer[r] + ex->flags_off) + slot * ex->world + ex->rank;
+    }
     return PVB_OK;
 }
 
@@ -234,24 +272,51 @@ PVB_API int pvb_workspace_layout(const pvb_desc *d, pvb_layout *out)
     return make_layout(d, out);
 }
 
-PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
-                         const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
-                         pvb_stream_t stream)
+static int run_v3(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs, const float *selection,
+                  float *out_kpt, void *workspace, size_t workspace_bytes, const float *seg, int32_t classes,
+                  int64_t class_stride, int64_t *mask_out, pvb_exchange *ex, uint64_t seq, cudaStream_t st)
 {
     Plan P;
-    int rc = make_plan(d, mask, vertex, idxs, selection, workspace, workspace_bytes, 1u, 2u, &P);
+    int rc = make_plan(d, seg ? static_cast<const void *>(seg) : mask, vertex, idxs, selection, workspace, workspace_bytes, 1u, 2u, &P);
     if (rc) return rc;
     if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
-    if (d->B == 0) return PVB_OK;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PeerPush pp;
+    rc = exchange_push_args(ex, seq, (size_t)d->B * d->K * 2 * sizeof(float), P.done, &pp);
+    if (rc) return rc;
+    if (d->B == 0) {
+        if (pp.world > 0) return fail(PVB_ERR_INVALID, "an exchanging call needs B >= 1 on every rank");
+        return PVB_OK;
+    }
+    if (seg) {
+        P.s.seg_classes = classes;
+        P.s.seg_cs = class_stride;
+        P.s.mask_out = reinterpret_cast<long long *>(mask_out);
+    }
     ProfCall *pc = prof_begin(true);
     rc = run_front(P, st, pc);
     if (rc) return rc;
     prof_start(pc, PVB_STAGE_FINISH, st);
-    cudaError_t e = launch_refit(P.v, P.win, P.refit, out_kpt, st);
+    cudaError_t e = launch_refit(P.v, P.win, P.refit, out_kpt, pp, st);
     if (e != cudaSuccess) return cuda_fail(e, "refit kernel");
     prof_end(pc, PVB_STAGE_FINISH, st);
     return PVB_OK;
+}
+
+PVB_API int pvb_ransac_voting_v3(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
+                         const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
+                         pvb_stream_t stream)
+{
+    return run_v3(d, mask, vertex, idxs, selection, out_kpt, workspace, workspace_bytes, nullptr, 0, 0, nullptr, nullptr, 0,
+                  static_cast<cudaStream_t>(stream));
+}
+
+PVB_API int pvb_ransac_voting_v3_push(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
+                                      const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
+                                      pvb_exchange *exchange, uint64_t seq, pvb_stream_t stream)
+{
+    if (!exchange) return fail(PVB_ERR_INVALID, "exchange is NULL");
+    return run_v3(d, mask, vertex, idxs, selection, out_kpt, workspace, workspace_bytes, nullptr, 0, 0, nullptr, exchange, seq,
+                  static_cast<cudaStream_t>(stream));
 }
 
 PVB_API int pvb_decode_v3(const pvb_desc *d, const float *seg, int32_t classes, int64_t class_stride, int64_t *mask_out,
@@ -259,23 +324,9 @@ PVB_API int pvb_decode_v3(const pvb_desc *d, const float *seg, int32_t classes, 
                           void *workspace, size_t workspace_bytes, pvb_stream_t stream)
 {
     if (classes < 1 || classes > 4096) return fail(PVB_ERR_INVALID, "classes must be in [1,4096]");
-    Plan P;
-    int rc = make_plan(d, seg, vertex, idxs, selection, workspace, workspace_bytes, 1u, 2u, &P);
-    if (rc) return rc;
-    if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
-    if (d->B == 0) return PVB_OK;
-    P.s.seg_classes = classes;
-    P.s.seg_cs = class_stride;
-    P.s.mask_out = reinterpret_cast<long long *>(mask_out);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ProfCall *pc = prof_begin(true);
-    rc = run_front(P, st, pc);
-    if (rc) return rc;
-    prof_start(pc, PVB_STAGE_FINISH, st);
-    cudaError_t e = launch_refit(P.v, P.win, P.refit, out_kpt, st);
-    if (e != cudaSuccess) return cuda_fail(e, "refit kernel");
-    prof_end(pc, PVB_STAGE_FINISH, st);
-    return PVB_OK;
+    if (!seg) return fail(PVB_ERR_INVALID, "seg is NULL");
+    return run_v3(d, nullptr, vertex, idxs, selection, out_kpt, workspace, workspace_bytes, seg, classes, class_stride, mask_out,
+                  nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
@@ -387,55 +438,93 @@ static int host_slot_layout(const pvb_desc *d, int chunk, HostSlot *S, pvb_desc 
     return PVB_OK;
 }
 
+constexpr int HOST_SLOTS = 4;     // pieces in flight: the mask DMA runs up to HOST_SLOTS-1 pieces ahead of the compute
+
 PVB_API size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images)
 {
     HostSlot S; pvb_desc dc;
     if (check_desc(d) || host_slot_layout(d, chunk_images, &S, &dc)) return 0;
-    return 2 * S.end;
+    return HOST_SLOTS * S.end;
 }
 
+namespace {
+// streams and events of the host pipeline: one set per (host thread, device), created on first use and kept
+struct HostPipe {
+    cudaStream_t copy = nullptr, in = nullptr, cmp = nullptr;
+    cudaEvent_t user = nullptr, end = nullptr, dma[HOST_SLOTS] = {}, sel[HOST_SLOTS] = {}, done[HOST_SLOTS] = {};
+    bool ready = false;
+};
+constexpr int MAX_DEVICES = 64;
+
+int host_pipe(int dev, HostPipe **out)
+{
+    static thread_local HostPipe pipes[MAX_DEVICES];
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(PVB_ERR_CUDA, "device index %d out of range", dev);
+    HostPipe &p = pipes[dev];
+    if (!p.ready) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least, hi = greatest priority (numerically lower)
+        cudaError_t e = cudaStreamCreateWithPriority(&p.copy, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p.in, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p.cmp, cudaStreamNonBlocking, lo);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        cudaEvent_t *single[] = {&p.user, &p.end};
+        for (cudaEvent_t *pe : single)
+            if ((e = cudaEventCreateWithFlags(pe, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        for (int i = 0; i < HOST_SLOTS; ++i) {
+            e = cudaEventCreateWithFlags(&p.dma[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.sel[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        }
+        p.ready = true;
+    }
+    *out = &p;
+    return PVB_OK;
+}
+
+// device-visible alias of a pinned host pointer, or NULL when `p` is not mapped host memory
+const void *mapped_alias(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return a.devicePointer;
+}
+} // namespace
+
 PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
-                              float *out_kpt_host, int32_t chunk_images, void *dev_scratch, size_t dev_scratch_bytes,
-                              pvb_stream_t stream)
+                              float *out_kpt_host, int32_t chunk_images, uint32_t flags, void *dev_scratch,
+                              size_t dev_scratch_bytes, pvb_stream_t stream)
 {
     int rc = check_desc(d);
     if (rc) return rc;
     if (!mask_host || !vertex_host || !out_kpt_host) return fail(PVB_ERR_INVALID, "host buffer is NULL");
+    if (flags & ~(uint32_t)(PVB_HOST_INPLACE_MASK | PVB_HOST_STAGE_VERTEX)) return fail(PVB_ERR_INVALID, "unknown flags 0x%x", flags);
     HostSlot S; pvb_desc dc;
     rc = host_slot_layout(d, chunk_images, &S, &dc);
     if (rc) return rc;
-    if (!dev_scratch || dev_scratch_bytes < 2 * S.end) return fail(PVB_ERR_WORKSPACE, "device scratch too small: need %zu", 2 * S.end);
+    if (!dev_scratch || dev_scratch_bytes < HOST_SLOTS * S.end) return fail(PVB_ERR_WORKSPACE, "device scratch too small: need %zu", HOST_SLOTS * S.end);
     if (reinterpret_cast<uintptr_t>(dev_scratch) & 255u) return fail(PVB_ERR_WORKSPACE, "device scratch must be 256-byte aligned");
-    // Two-stage software pipeline over `chunk_images`-sized pieces, double-buffered in dev_scratch:
-    //   stage A (high-priority stream): bring the piece in -- staged H2D copies, or (zero-copy) let mask_bits and
-    //            gather read the pinned host tensors in place -- and run the select kernels;   PCIe-bound
-    //   stage B (low-priority stream):  generate, vote, refit, D2H of the keypoints;          SM-bound
-    // Stage A of piece i+1 overlaps stage B of piece i; the priority lets the bus-bound CTAs slip in as vote
-    // CTAs retire.
-    static thread_local cudaStream_t s_in = nullptr, s_cmp = nullptr;
-    static thread_local cudaEvent_t ev_user = nullptr, ev_sel[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr},
-                                    ev_end = nullptr;
-    static thread_local int streams_dev = -1;
+    // Software pipeline over `chunk_images`-sized pieces, HOST_SLOTS of them in flight, on three streams:
+    //   copy (high priority): cudaMemcpyAsync of whatever is STAGED (by default the mask: one contiguous DMA per piece at the
+    //                         copy engine's PCIe rate); runs ahead of the kernels as far as the slot ring allows
+    //   in   (high priority): the select kernels; whatever is NOT staged is read in place from the pinned host tensor
+    //                         (by default the vertex field: gather fetches only the SELECTED pixels' rows, tn*K*8 bytes
+    //                         per image instead of the dense H*W*K*8)
+    //   cmp  (low priority):  generate, vote, refit, D2H of the keypoints
+    // Both PCIe consumers (DMA and in-place reads) share the link, so the pipeline's job is to keep it busy end to end.
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    if (streams_dev != dev) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least, hi = greatest priority (numerically lower)
-        e = cudaStreamCreateWithPriority(&s_in, cudaStreamNonBlocking, hi);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_cmp, cudaStreamNonBlocking, lo);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-        cudaEvent_t *evs[] = {&ev_user, &ev_sel[0], &ev_sel[1], &ev_cmp[0], &ev_cmp[1], &ev_end};
-        for (cudaEvent_t *pe : evs) {
-            e = cudaEventCreateWithFlags(pe, cudaEventDisableTiming);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
-        }
-        streams_dev = dev;
-    }
+    HostPipe *hp = nullptr;
+    rc = host_pipe(dev, &hp);
+    if (rc) return rc;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
-    e = cudaEventRecord(ev_user, user);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_in, ev_user, 0);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_cmp, ev_user, 0);
+    e = cudaEventRecord(hp->user, user);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->copy, hp->user, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->in, hp->user, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->cmp, hp->user, 0);
     if (e != cudaSuccess) return cuda_fail(e, "stream wait");
     const size_t HW = (size_t)d->H * d->W;
     const size_t mbytes = HW * mask_elt_bytes(d->mask_dtype), vbytes = HW * d->K * 2 * sizeof(float);
@@ -444,37 +533,37 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
     pvb_layout Lc;
     rc = make_layout(&dc, &Lc);
     if (rc) return rc;
-    // Zero-copy: when both inputs are pinned (device-mapped) host memory the kernels read them in place over
-    // PCIe -- the mask is streamed once by mask_bits, and gather fetches ONLY the selected pixels' rows
-    // (tn*K*8 bytes per image instead of the dense H*W*K*8), so the dense vertex field never crosses the bus.
-    bool zero_copy = g_host_zero_copy;
-    if (zero_copy) {
-        cudaPointerAttributes am, av;
-        if (cudaPointerGetAttributes(&am, mask_host) != cudaSuccess || cudaPointerGetAttributes(&av, vertex_host) != cudaSuccess ||
-            am.type != cudaMemoryTypeHost || av.type != cudaMemoryTypeHost || !am.devicePointer || !av.devicePointer) {
-            zero_copy = false;
-            cudaGetLastError();   // clear the sticky "invalid value" of an unregistered pointer
-        }
-    }
-    int slot = 0, piece = 0;
-    for (int b0 = 0; b0 < d->B; b0 += chunk_images, slot ^= 1, ++piece) {
+    // in-place reads need pinned, device-mapped host memory; anything else is staged
+    const char *mask_alias = static_cast<const char *>(mapped_alias(mask_host));
+    const char *vertex_alias = static_cast<const char *>(mapped_alias(vertex_host));
+    const bool stage_mask = !(flags & PVB_HOST_INPLACE_MASK) || !mask_alias;
+    const bool stage_vertex = (flags & PVB_HOST_STAGE_VERTEX) || !vertex_alias;
+    int piece = 0;
+    for (int b0 = 0; b0 < d->B; b0 += chunk_images, ++piece) {
+        const int slot = piece % HOST_SLOTS;
         const int c = (d->B - b0 < chunk_images) ? d->B - b0 : chunk_images;
         char *sb = base + (size_t)slot * S.end;
         const void *mptr = sb + S.mask;
         const float *vptr = reinterpret_cast<const float *>(sb + S.vertex);
-        // this slot's buffers are free once the piece that used them two steps ago has been computed
-        if (piece >= 2) {
-            e = cudaStreamWaitEvent(s_in, ev_cmp[slot], 0);
+        // this slot's buffers are free once the piece that used them HOST_SLOTS pieces ago has been computed
+        if (piece >= HOST_SLOTS) {
+            e = cudaStreamWaitEvent(hp->copy, hp->done[slot], 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->in, hp->done[slot], 0);
             if (e != cudaSuccess) return cuda_fail(e, "stream wait");
         }
-        if (zero_copy) {
-            mptr = static_cast<const char *>(mask_host) + (size_t)b0 * mbytes;
-            vptr = reinterpret_cast<const float *>(reinterpret_cast<const char *>(vertex_host) + (size_t)b0 * vbytes);
-        } else {
-            e = cudaMemcpyAsync(sb + S.mask, static_cast<const char *>(mask_host) + (size_t)b0 * mbytes, (size_t)c * mbytes, cudaMemcpyHostToDevice, s_in);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync(sb + S.vertex, reinterpret_cast<const char *>(vertex_host) + (size_t)b0 * vbytes, (size_t)c * vbytes, cudaMemcpyHostToDevice, s_in);
-            if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+        if (stage_mask)
+            e = cudaMemcpyAsync(sb + S.mask, static_cast<const char *>(mask_host) + (size_t)b0 * mbytes, (size_t)c * mbytes, cudaMemcpyHostToDevice, hp->copy);
+        else
+            mptr = mask_alias + (size_t)b0 * mbytes;
+        if (e == cudaSuccess && stage_vertex)
+            e = cudaMemcpyAsync(sb + S.vertex, reinterpret_cast<const char *>(vertex_host) + (size_t)b0 * vbytes, (size_t)c * vbytes, cudaMemcpyHostToDevice, hp->copy);
+        else if (e == cudaSuccess)
+            vptr = reinterpret_cast<const float *>(vertex_alias + (size_t)b0 * vbytes);
+        if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+        if (stage_mask || stage_vertex) {
+            e = cudaEventRecord(hp->dma[slot], hp->copy);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->in, hp->dma[slot], 0);
+            if (e != cudaSuccess) return cuda_fail(e, "pipeline event");
         }
         pvb_desc di = dc;
         di.B = c;
@@ -483,30 +572,30 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
         Plan P;
         rc = make_plan(&di, mptr, vptr, nullptr, nullptr, sb + S.ws, S.end - S.ws, 1u, 2u, &P);
         if (rc) return rc;
-        P.s.rowwise_gather = zero_copy ? 1 : 0;
-        rc = run_select(P, s_in);                                   // stage A
+        P.s.rowwise_gather = stage_vertex ? 0 : 1;
+        rc = run_select(P, hp->in);
         if (rc) return rc;
-        e = cudaEventRecord(ev_sel[slot], s_in);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_cmp, ev_sel[slot], 0);
+        e = cudaEventRecord(hp->sel[slot], hp->in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->cmp, hp->sel[slot], 0);
         if (e != cudaSuccess) return cuda_fail(e, "pipeline event");
-        e = launch_generate(P.v, s_cmp);                            // stage B
-        if (e == cudaSuccess) e = launch_vote(P.v, s_cmp);
-        if (e == cudaSuccess) e = launch_refit(P.v, P.win, P.refit, reinterpret_cast<float *>(sb + S.out), s_cmp);
+        PeerPush none;
+        memset(&none, 0, sizeof(none));
+        e = launch_generate(P.v, hp->cmp);
+        if (e == cudaSuccess) e = launch_vote(P.v, hp->cmp);
+        if (e == cudaSuccess) e = launch_refit(P.v, P.win, P.refit, reinterpret_cast<float *>(sb + S.out), none, hp->cmp);
         if (e != cudaSuccess) return cuda_fail(e, "compute kernels");
-        e = cudaMemcpyAsync(reinterpret_cast<char *>(out_kpt_host) + (size_t)b0 * obytes, sb + S.out, (size_t)c * obytes, cudaMemcpyDeviceToHost, s_cmp);
-        if (e == cudaSuccess) e = cudaEventRecord(ev_cmp[slot], s_cmp);
+        e = cudaMemcpyAsync(reinterpret_cast<char *>(out_kpt_host) + (size_t)b0 * obytes, sb + S.out, (size_t)c * obytes, cudaMemcpyDeviceToHost, hp->cmp);
+        if (e == cudaSuccess) e = cudaEventRecord(hp->done[slot], hp->cmp);
         if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
     }
-    e = cudaEventRecord(ev_end, s_cmp);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ev_end, 0);
+    e = cudaEventRecord(hp->end, hp->cmp);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(user, hp->end, 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(user);
     if (e != cudaSuccess) return cuda_fail(e, "stream sync");
     return PVB_OK;
 }
 
 PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK; }
-
-PVB_API int pvb_set_host_mode(int32_t zero_copy) { g_host_zero_copy = zero_copy != 0; return PVB_OK; }
 
 PVB_API int pvb_set_tuning(int32_t vote_chunk, int32_t vote_variant)
 {
@@ -637,6 +726,115 @@ PVB_API int pvb_vote_count(const float *direct, const float *coords, const float
     if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
     e = launch_compat_unpack_counts(counts_k, counts, vn, hn, st);
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "unpack");
+}
+
+// ---- multi-GPU exchange ----------------------------------------------------------------
+PVB_API int pvb_exchange_create(int32_t rank, int32_t world, int32_t slots, size_t bytes_per_rank, pvb_exchange **out)
+{
+    if (!out) return fail(PVB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > PVB_MAX_PEERS || rank < 0 || rank >= world) return fail(PVB_ERR_INVALID, "bad rank %d / world %d (max %d)", rank, world, PVB_MAX_PEERS);
+    if (slots < 2 || slots > 4096) return fail(PVB_ERR_INVALID, "slots must be in [2,4096]");
+    if (bytes_per_rank == 0 || bytes_per_rank > ((size_t)1 << 30)) return fail(PVB_ERR_INVALID, "bad bytes_per_rank");
+    pvb_exchange *ex = new (std::nothrow) pvb_exchange();
+    if (!ex) return fail(PVB_ERR_INVALID, "out of host memory");
+    memset(ex, 0, sizeof(*ex));
+    ex->rank = rank; ex->world = world; ex->slots = slots;
+    ex->bytes_per_rank = (bytes_per_rank + 15) / 16 * 16;
+    ex->flags_off = align_up((size_t)slots * world * ex->bytes_per_rank);
+    ex->status_off = align_up(ex->flags_off + (size_t)slots * world * sizeof(unsigned long long));
+    ex->total = ex->status_off + 256;
+    cudaError_t e = cudaGetDevice(&ex->device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ex->local), ex->total);
+    if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->total);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { if (ex->local) cudaFree(ex->local); delete ex; return cuda_fail(e, "exchange allocation"); }
+    ex->peer[rank] = ex->local;
+    ex->connected = (world == 1);
+    *out = ex;
+    return PVB_OK;
+}
+
+PVB_API size_t pvb_exchange_bytes_per_rank(const pvb_exchange *ex) { return ex ? ex->bytes_per_rank : 0; }
+PVB_API void *pvb_exchange_base(const pvb_exchange *ex) { return ex ? ex->local : nullptr; }
+
+PVB_API int pvb_exchange_get_handle(const pvb_exchange *ex, void *handle)
+{
+    if (!ex || !handle) return fail(PVB_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PVB_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ex->local);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+    memcpy(handle, &h, sizeof(h));
+    return PVB_OK;
+}
+
+PVB_API int pvb_exchange_connect_ptrs(pvb_exchange *ex, void *const *bases)
+{
+    if (!ex || !bases) return fail(PVB_ERR_INVALID, "NULL argument");
+    for (int r = 0; r < ex->world; ++r) {
+        if (r == ex->rank) continue;
+        if (!bases[r]) return fail(PVB_ERR_INVALID, "base pointer of rank %d is NULL", r);
+        ex->peer[r] = static_cast<char *>(bases[r]);
+    }
+    ex->connected = true;
+    return PVB_OK;
+}
+
+PVB_API int pvb_exchange_connect(pvb_exchange *ex, const void *handles)
+{
+    if (!ex || !handles) return fail(PVB_ERR_INVALID, "NULL argument");
+    const char *hb = static_cast<const char *>(handles);
+    for (int r = 0; r < ex->world; ++r) {
+        if (r == ex->rank || ex->ipc_opened[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hb + (size_t)r * PVB_IPC_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer memory over NVLink needs P2P access between the GPUs)");
+        ex->peer[r] = static_cast<char *>(p);
+        ex->ipc_opened[r] = true;
+    }
+    ex->connected = true;
+    return PVB_OK;
+}
+
+PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, double timeout_s, pvb_stream_t stream)
+{
+    if (!ex || !out) return fail(PVB_ERR_INVALID, "NULL argument");
+    if (seq == 0) return fail(PVB_ERR_INVALID, "seq must be >= 1");
+    if (reinterpret_cast<uintptr_t>(out) & 15u) return fail(PVB_ERR_INVALID, "out must be 16-byte aligned");
+    if (!(timeout_s > 0.0)) timeout_s = 10.0;
+    const size_t slot = (size_t)((seq - 1) % (uint64_t)ex->slots);
+    const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(ex->local + ex->flags_off) + slot * ex->world;
+    const char *recv = ex->local + slot * ex->world * ex->bytes_per_rank;
+    cudaError_t e = launch_exchange_wait(flags, seq, recv, out, (size_t)ex->world * ex->bytes_per_rank / 16, ex->world,
+                                         (unsigned long long)(timeout_s * 1e9), reinterpret_cast<int *>(ex->local + ex->status_off),
+                                         static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "exchange wait kernel");
+}
+
+PVB_API int pvb_exchange_status(pvb_exchange *ex, pvb_stream_t stream)
+{
+    if (!ex) return fail(PVB_ERR_INVALID, "NULL argument");
+    int host = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(&host, ex->local + ex->status_off, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "exchange status");
+    if (host) return fail(PVB_ERR_TIMEOUT, "a pvb_exchange_wait timed out: some rank never published its result");
+    return PVB_OK;
+}
+
+PVB_API int pvb_exchange_destroy(pvb_exchange *ex)
+{
+    if (!ex) return PVB_OK;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ex->world; ++r)
+        if (ex->ipc_opened[r]) cudaIpcCloseMemHandle(ex->peer[r]);
+    if (ex->local) cudaFree(ex->local);
+    delete ex;
+    return PVB_OK;
 }
 
 } // extern "C"

@@ -92,7 +92,6 @@ struct ConeParams {
     float kappa;   // tan(acos(thresh)) = sqrt(1-t^2)/t
     float band;    // guard band per unit of S = |hx-ox|+|hy-oy|+cmax(tile) ; +inf => exact path only
     float thresh;  // (float)inlier_thresh
-    float band_mma;  // guard band of the tensor-path vote kernel, in the scaled domain (m*s, S*s < 1)
 };
 
 } // namespace pvb

@@ -52,7 +52,24 @@ void set_vote_tuning(int variant);   // tooling: pixel-tile size per CTA
 // them in a fixed order and solves, so the result is deterministic.
 struct RefitScratch { double *partial; int *ticket; int splits; };
 int refit_splits_for(int cap);
-cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, cudaStream_t st);
+// Multi-GPU result exchange fused into the refit kernel: the CTA that completes the LAST (image,keypoint) of
+// the call stores the rank's whole [B][K][2] result into every peer's receive slot over NVLink (plain peer stores) and then
+// publishes `seq` in every peer's flag word; nobody waits here (pvb_exchange_wait does, later, on the consumer's stream).
+constexpr int PVB_MAX_PEERS = 16;
+struct PeerPush {
+    int world;                                  // 0: no exchange
+    int nfloats;                                // B*K*2
+    unsigned long long seq;                     // value published in the flags (monotonic per exchange)
+    int *done;                                  // workspace counter, zeroed per call: (image,keypoint) results written
+    float *recv[PVB_MAX_PEERS];                 // peer r: where THIS rank's slice of the current slot lives in r's memory
+    unsigned long long *flag[PVB_MAX_PEERS];    // peer r: flag word of (current slot, this rank)
+};
+cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, const PeerPush &pp,
+                         cudaStream_t st);
+// spins (bounded by timeout_ns) until flags[r] >= seq for r < world, then copies n16 16-byte words recv -> out;
+// on timeout sets *status = 1 and fills `out` with NaN
+cudaError_t launch_exchange_wait(const unsigned long long *flags, unsigned long long seq, const void *recv, void *out,
+                                 size_t n16, int world, unsigned long long timeout_ns, int *status, cudaStream_t st);
 // ratio/threshold/weighted covariance -> out_cov [B][K][2][2]
 cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, cudaStream_t st);
 

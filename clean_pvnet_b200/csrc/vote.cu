@@ -21,8 +21,9 @@
 //     whose smallest |m| falls inside it are re-evaluated -- warp-cooperatively -- with the
 //     reference's exact operation sequence (vote_exact).  Counts equal the reference's.
 //
-// vote_mma_kernel (further down) is an opt-in experiment, not the shipped path: the same margin through mma.sync (tf32 x 3
-// split) -- see the comment above it, DESIGN.md 4.2 and profiles/r01_vote_tuning.md.
+// No tensor cores: the specification of this path excludes them (a sparse reduction, not a dense contraction).  Round 1
+// measured what an mma.sync formulation would buy (+8 %); the write-up is profiles/r01_vote_tuning.md, the kernel is gone.
+#include <atomic>
 #include <math_constants.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -267,323 +268,12 @@ vote_kernel(const VoteK p)
     }
 }
 
-// ---------------------------------------------------------------------------------
-// the vote kernel on the warp-level tensor path (mma.sync m16n8k8, tf32 x 3 split)
-//
-// Both dot products of the cone margin are rank-3 bilinear forms in (pixel record, hypothesis):
-//     kappa*a = (A1,A2,A3).(hx,hy,1)      p = (B1,B2,B3).(hx,hy,1)
-// Every fp32 factor is split into two tf32 numbers, x = xh + xl (round-to-nearest, |xl| <= 2^-11 |x|, the second
-// split leaves <= 2^-22 |x|), and each hypothesis column is pre-scaled by a power of two s = 2^-e, 2^e > S (exact),
-// so that the 8 k-slots of one MMA hold
-//     slot 0: A1h*hxh   1: A2h*hyh   2: A1h*hxl   3: A3h*s   4: A1l*hxh   5: A2l*hyh   6: A2h*hyl   7: A3l*s
-// (xl*xl terms dropped).  One MMA pair scores 16 pixels x 8 hypotheses; what is left for the FP32/ALU pipes per
-// test is  m = P - |Q|  (FADD),  the sign-bit tally (LEA.HI)  and half an FMNMX3 for the guard band, which in the
-// scaled domain is one constant (|m*s| < band_mma  <=  |m| < band_mma*S since S*s < 1).  Tests inside the band are
-// re-evaluated with the reference's exact operation sequence, so counts still equal the reference's.
-// Fragment layout (PTX ISA, m16n8k8 .tf32; g = lane>>2, t = lane&3; checked by tools/microbench3.cu):
-//   A: a0=(row g, k t)  a1=(row g+8, k t)  a2=(row g, k t+4)  a3=(row g+8, k t+4)
-//   B: b0=(k t, col g)  b1=(k t+4, col g)          D: d0=(g,2t) d1=(g,2t+1) d2=(g+8,2t) d3=(g+8,2t+1)
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_rna(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const float4 a, float b0, float b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-                 : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
-                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(0.f));
-}
-
-// Guard-band settlement of one thread's 2x2 results of an MMA pair (rows px, px+8; columns h, h+1): every margin inside
-// the band is replaced by the verdict of the reference's exact operation sequence.  Returns the corrections of the two
-// column tallies packed as (column h+1) << 16 | (column h) & 0xffff, each in [-2, 2].  Out of line on purpose.
-__device__ __noinline__ int settle_in_band(float m0, float m1, float m2, float m3, float bandn, int px, int h, int n, int hn,
-                                           const float2 *__restrict__ dk, const float2 *__restrict__ xy,
-                                           const float2 *__restrict__ hyp, float thresh)
-{
-    const float m[4] = { m0, m1, m2, m3 };
-    int d0 = 0, d1 = 0;
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const float mi = (i == 0) ? m[0] : (i == 1) ? m[1] : (i == 2) ? m[2] : m[3];
-        if (!(fabsf(mi) >= bandn)) {
-            const int p_ = px + (i >> 1) * 8, h_ = h + (i & 1);
-            bool in = false;      // padding rows and columns past hn: "not an inlier" (their tallies are never used)
-            if (p_ < n && h_ < hn) {
-                const float2 vv = __ldg(dk + p_), cc = __ldg(xy + p_), q = __ldg(hyp + h_);
-                in = vote_exact(vv.x, vv.y, cc.x, cc.y, q.x, q.y, thresh);
-            }
-            const int delta = (in ? 0 : 1) - (int)(__float_as_uint(mi) >> 31);
-            if (i & 1) d1 += delta; else d0 += delta;
-        }
-    }
-    return (d1 << 16) | (d0 & 0xffff);
-}
-
-// NTW = 8-hypothesis column tiles per warp (one "group" = 8*NTW hypotheses).  A CTA of NWARP warps covers
-// min(groups, NWARP) groups (rounded up to a power of two); if that leaves warps over, they form further teams
-// that split the tile's 16-pixel blocks, exactly like vote_kernel.
-template <int NTW, int NWARP, int MINB, int VOTE_TILE>
-__global__ void __launch_bounds__(NWARP * 32, MINB)
-vote_mma_kernel(const VoteK p, const int gpc /* groups per CTA, power of two <= NWARP */)
-{
-    constexpr int NT = NWARP * 32;
-    static_assert(VOTE_TILE % (2 * NWARP * 32) == 0, "tile = whole pixel pairs per thread");
-    constexpr int PPT = VOTE_TILE / NT;               // pixels staged per thread (rows g and g+8 of the same block)
-    constexpr int NBLK = VOTE_TILE / VOTE_BLOCK;
-    constexpr int GH = 8 * NTW;                       // hypotheses per group (= per warp)
-    constexpr int HPT = (NWARP * GH + NT - 1) / NT;   // hypotheses staged per thread
-    // dynamic shared memory: A fragments of both forms [block][slot], slot = g*4 + (t ^ (g>>1)) holding lane (g,t)'s
-    // float4 (a0..a3) -- the XOR makes both the consumer's LDS.128 (quarter warp = 2 g x 4 t) and the producer's
-    // STS.128 (quarter warp = 8 g, one t) hit 8 different 16-byte bank groups; then the CTA's B fragments
-    // [hypothesis][t] = (b0,b1), then the bounding-box scratch
-    extern __shared__ __align__(16) float4 s_dyn[];
-    float4 *s_p = s_dyn, *s_q = s_dyn + NBLK * 32;
-    float2 *s_h = reinterpret_cast<float2 *>(s_dyn + 2 * NBLK * 32);
-    float *s_box = reinterpret_cast<float *>(s_h + NWARP * GH * 4);
-    const VoteArgs &a = p.a;
-    const int b = blockIdx.z;
-    const int k = blockIdx.y % a.K, chunk = blockIdx.y / a.K;
-    const int tn = min(a.tn[b], a.cap);
-    const int t0 = blockIdx.x * VOTE_TILE;
-    if (t0 >= tn) return;
-    const int n = min(VOTE_TILE, tn - t0);
-    const int nblk = (n + VOTE_BLOCK - 1) / VOTE_BLOCK;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const float kappa = p.cone.kappa, thresh = p.cone.thresh;
-    const float2 *hyp = a.hyp + ((size_t)b * a.K + k) * a.hn;
-    const float2 *xy = a.xy + (size_t)b * a.cap + t0;
-    const float2 *dk = a.dirs + ((size_t)b * a.K + k) * a.cap + t0;
-    const int hyp0 = chunk * gpc * GH;                // first hypothesis of this CTA
-
-    // ---- stage 1: load this tile's pixels and this CTA's hypotheses; bounding box -> tile-local origin
-    // thread <-> pixels: pair pr = tid (+NT, ...) covers rows g8 = pr&7 and g8+8 of block pr>>3, i.e. pixels i and i+8
-    float2 v[PPT], c[PPT], hq[HPT];
-    float x0 = CUDART_INF_F, x1 = -CUDART_INF_F, y0 = CUDART_INF_F, y1 = -CUDART_INF_F;
-#pragma unroll
-    for (int r = 0; r < PPT; ++r) {
-        const int pr = tid + (r >> 1) * NT;
-        const int i = (pr >> 3) * VOTE_BLOCK + (pr & 7) + (r & 1) * 8;
-        v[r] = make_float2(0.f, 0.f); c[r] = make_float2(0.f, 0.f);
-        if (i < n) {
-            v[r] = __ldg(dk + i); c[r] = __ldg(xy + i);
-            x0 = fminf(x0, c[r].x); x1 = fmaxf(x1, c[r].x); y0 = fminf(y0, c[r].y); y1 = fmaxf(y1, c[r].y);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < HPT; ++r) {
-        const int hl = tid + r * NT;
-        hq[r] = (hl < gpc * GH && hyp0 + hl < a.hn) ? __ldg(hyp + hyp0 + hl) : make_float2(CUDART_NAN_F, 0.f);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-    }
-    if (lane == 0) { s_box[warp] = x0; s_box[NWARP + warp] = x1; s_box[2 * NWARP + warp] = y0; s_box[3 * NWARP + warp] = y1; }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) {
-        x0 = fminf(x0, s_box[w]); x1 = fmaxf(x1, s_box[NWARP + w]);
-        y0 = fminf(y0, s_box[2 * NWARP + w]); y1 = fmaxf(y1, s_box[3 * NWARP + w]);
-    }
-    const float ox = 0.5f * (x0 + x1), oy = 0.5f * (y0 + y1);
-    const float cmax = (0.5f * (x1 - x0) + 0.5f * (y1 - y0)) * 1.000001f + 1e-3f;
-
-    // ---- stage 2a: cone records (same values as vote_kernel), split and stored in fragment order
-#pragma unroll
-    for (int r = 0; r < PPT; r += 2) {
-        const int pr = tid + (r >> 1) * NT;
-        const int blk = pr >> 3, g8 = pr & 7;
-        if (blk < nblk) {
-            float ph[2][3], pl[2][3], qh[2][3], ql[2][3];     // [row g8 / g8+8][coefficient 1..3], tf32 high and low parts
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int i = blk * VOTE_BLOCK + g8 + e * 8;
-                float A1 = 0.f, A2 = 0.f, A3 = -1e30f, B1 = 0.f, B2 = 0.f, B3 = 0.f;   // pad: never votes, never in the band
-                if (i < n) {
-                    const float2 vv = v[r + e], cc = c[r + e];
-                    const float n1 = __fsqrt_rn(__fmaf_rn(vv.x, vv.x, __fmul_rn(vv.y, vv.y)));
-                    const float cxc = cc.x - ox, cyc = cc.y - oy;
-                    if (!(n1 > below_1e6())) {
-                        // the reference never votes for this pixel (.cu:121)
-                    } else if (!(n1 < 1e18f) || !(fabsf(cxc) + fabsf(cyc) <= cmax)) {
-                        A3 = 0.f;                                  // m == 0: inside every band -> exact path
-                    } else {
-                        const float inv = 1.0f / n1;
-                        const float ux = vv.x * inv, uy = vv.y * inv;
-                        A1 = kappa * ux; A2 = kappa * uy; A3 = -fmaf(A1, cxc, A2 * cyc);
-                        B1 = -uy; B2 = ux; B3 = fmaf(uy, cxc, -(ux * cyc));
-                    }
-                }
-                ph[e][0] = tf32_rna(A1); ph[e][1] = tf32_rna(A2); ph[e][2] = tf32_rna(A3);
-                qh[e][0] = tf32_rna(B1); qh[e][1] = tf32_rna(B2); qh[e][2] = tf32_rna(B3);
-                pl[e][0] = tf32_rna(A1 - ph[e][0]); pl[e][1] = tf32_rna(A2 - ph[e][1]); pl[e][2] = tf32_rna(A3 - ph[e][2]);
-                ql[e][0] = tf32_rna(B1 - qh[e][0]); ql[e][1] = tf32_rna(B2 - qh[e][1]); ql[e][2] = tf32_rna(B3 - qh[e][2]);
-            }
-            // lane (g8, t=q): (a0,a1,a2,a3) = (row g8 k q, row g8+8 k q, row g8 k q+4, row g8+8 k q+4)
-            float4 *dp = s_p + blk * 32 + g8 * 4, *dq = s_q + blk * 32 + g8 * 4;
-            const int x = g8 >> 1;
-            dp[0 ^ x] = make_float4(ph[0][0], ph[1][0], pl[0][0], pl[1][0]);   // k 0,4: A1h*hxh + A1l*hxh
-            dp[1 ^ x] = make_float4(ph[0][1], ph[1][1], pl[0][1], pl[1][1]);   // k 1,5: A2h*hyh + A2l*hyh
-            dp[2 ^ x] = make_float4(ph[0][0], ph[1][0], ph[0][1], ph[1][1]);   // k 2,6: A1h*hxl + A2h*hyl
-            dp[3 ^ x] = make_float4(ph[0][2], ph[1][2], pl[0][2], pl[1][2]);   // k 3,7: A3h*s   + A3l*s
-            dq[0 ^ x] = make_float4(qh[0][0], qh[1][0], ql[0][0], ql[1][0]);
-            dq[1 ^ x] = make_float4(qh[0][1], qh[1][1], ql[0][1], ql[1][1]);
-            dq[2 ^ x] = make_float4(qh[0][0], qh[1][0], qh[0][1], qh[1][1]);
-            dq[3 ^ x] = make_float4(qh[0][2], qh[1][2], ql[0][2], ql[1][2]);
-        }
-    }
-    // ---- stage 2b: B fragments of the CTA's hypotheses, relative to the tile origin and scaled by s, a tf32 number
-    // (11 significant bits, so A3*s needs no third product) with 0.99 < S*s < 1:  |m*s| < band_mma  <=  |m| < band_mma*S
-#pragma unroll
-    for (int r = 0; r < HPT; ++r) {
-        const int hl = tid + r * NT;
-        if (hl < gpc * GH) {
-            float xc = hq[r].x - ox, yc = hq[r].y - oy, s = 1.f;
-            const float S = fabsf(xc) + fabsf(yc) + cmax;
-            if (hyp0 + hl >= a.hn) {
-                xc = 0.f; yc = 0.f;               // column past hn: harmless values, tally never used
-            } else if (S <= 1e15f) {
-                s = __uint_as_float(__float_as_uint(__fdividef(0.998f, S)) & 0xffffe000u);
-                xc *= s; yc *= s;
-            } else {
-                xc = 0.f; yc = 0.f; s = 0.f;      // outside the error analysis (or NaN): m == 0 everywhere -> exact path
-            }
-            const float hxh = tf32_rna(xc), hyh = tf32_rna(yc);
-            const float hxl = tf32_rna(xc - hxh), hyl = tf32_rna(yc - hyh);
-            float4 *dst = reinterpret_cast<float4 *>(s_h + hl * 4);
-            dst[0] = make_float4(hxh, hxh, hyh, hyh);      // t = 0: (slot 0, slot 4)   t = 1: (slot 1, slot 5)
-            dst[1] = make_float4(hxl, hyl, s, s);          // t = 2: (slot 2, slot 6)   t = 3: (slot 3, slot 7)
-        }
-    }
-    __syncthreads();
-
-    const int grp = warp & (gpc - 1);
-    const int team = warp / gpc, teams = NWARP / gpc;
-    const int hb = hyp0 + grp * GH;
-    if (hb >= a.hn) return;
-    float b0[NTW], b1[NTW];
-    int neg0[NTW], neg1[NTW];     // negative margins of columns 2t / 2t+1 over this thread's rows (g, g+8)
-#pragma unroll
-    for (int j = 0; j < NTW; ++j) {
-        const float2 bf = s_h[(grp * GH + j * 8 + g) * 4 + t];
-        b0[j] = bf.x; b1[j] = bf.y;
-        neg0[j] = 0; neg1[j] = 0;
-    }
-
-    const float bandn = p.cone.band_mma;
-    const uint32_t sp0 = (uint32_t)__cvta_generic_to_shared(s_p) + (g * 4 + (t ^ (g >> 1))) * 16;
-    const uint32_t sq0 = (uint32_t)__cvta_generic_to_shared(s_q) + (g * 4 + (t ^ (g >> 1))) * 16;
-
-    // one step = one 16-pixel block against this warp's 8*NTW hypotheses; returns whether any |margin| of this thread
-    // is inside the guard band.  (An FSETP...OR chain on one predicate instead of the FMNMX3 minimum measured 5 % slower.)
-    auto fast_step = [&](const float4 &pa, const float4 &qa) -> bool {
-        float mn = CUDART_INF_F;
-#pragma unroll
-        for (int j = 0; j < NTW; ++j) {
-            float cp[4], cq[4];
-            mma_tf32(cp, pa, b0[j], b1[j]);
-            mma_tf32(cq, qa, b0[j], b1[j]);
-            const float m0 = cp[0] - fabsf(cq[0]), m1 = cp[1] - fabsf(cq[1]);
-            const float m2 = cp[2] - fabsf(cq[2]), m3 = cp[3] - fabsf(cq[3]);
-            neg0[j] += (int)(__float_as_uint(m0) >> 31); neg0[j] += (int)(__float_as_uint(m2) >> 31);
-            neg1[j] += (int)(__float_as_uint(m1) >> 31); neg1[j] += (int)(__float_as_uint(m3) >> 31);
-            mn = fminf(mn, fminf(fabsf(m0), fabsf(m1)));      // FMNMX3 (ptxas fuses 2-input chains into it as well)
-            mn = fminf(mn, fminf(fabsf(m2), fabsf(m3)));
-        }
-        return !(mn >= bandn);
-    };
-    // rare (a few % of steps): some margin of the step is inside the guard band.  The MMAs are repeated (same inputs,
-    // same results) and every thread settles its own in-band tests with the reference's operation sequence.  Kept
-    // compact (one out-of-line exact routine) so that it costs no instruction-cache misses: the first version inlined
-    // 32 copies of vote_exact (184 KB of SASS) and ran 2x slower overall.
-    auto settle_step = [&](int blk, const float4 &pa, const float4 &qa) {
-        // phase 1, branch-free so that the MMAs overlap: which column tiles hold an in-band margin?
-        unsigned tiles = 0;
-#pragma unroll
-        for (int j = 0; j < NTW; ++j) {
-            float cp[4], cq[4];
-            mma_tf32(cp, pa, b0[j], b1[j]);
-            mma_tf32(cq, qa, b0[j], b1[j]);
-            const float mj = fminf(fminf(fabsf(cp[0] - fabsf(cq[0])), fabsf(cp[1] - fabsf(cq[1]))),
-                                   fminf(fabsf(cp[2] - fabsf(cq[2])), fabsf(cp[3] - fabsf(cq[3]))));
-            tiles |= !(mj >= bandn) ? (1u << j) : 0u;
-        }
-        // phase 2: settle those tiles (typically one tile, one thread, one test).  The tile mask is made warp-uniform
-        // first: mma.sync must be executed by all 32 lanes.
-        tiles = __reduce_or_sync(0xffffffffu, tiles);
-#pragma unroll
-        for (int j = 0; j < NTW; ++j) {
-            if (tiles & (1u << j)) {
-                float cp[4], cq[4];
-                mma_tf32(cp, pa, b0[j], b1[j]);
-                mma_tf32(cq, qa, b0[j], b1[j]);
-                const int px = blk * VOTE_BLOCK + g, h = hb + j * 8 + 2 * t;
-                const int d = settle_in_band(cp[0] - fabsf(cq[0]), cp[1] - fabsf(cq[1]), cp[2] - fabsf(cq[2]),
-                                             cp[3] - fabsf(cq[3]), bandn, px, h, n, a.hn, dk, xy, hyp, thresh);
-                neg0[j] += (int)(short)(d & 0xffff);
-                neg1[j] += d >> 16;
-            }
-        }
-    };
-
-    // two steps per iteration: the second block's fragments are in flight while the first is scored, and the
-    // loop / vote / branch overhead is paid once per 32 pixels
-    int mine = 0;
-    int blk = team;
-    for (; blk + teams < nblk; blk += 2 * teams) {
-        mine += 2 * VOTE_BLOCK;
-        const float4 pa0 = lds128(sp0 + blk * 512), qa0 = lds128(sq0 + blk * 512);
-        const float4 pa1 = lds128(sp0 + (blk + teams) * 512), qa1 = lds128(sq0 + (blk + teams) * 512);
-        const bool f0 = fast_step(pa0, qa0);
-        const bool f1 = fast_step(pa1, qa1);
-        if (__builtin_expect(__any_sync(0xffffffffu, f0 || f1), 0)) {
-#pragma unroll 1
-            for (int e = 0; e < 2; ++e) {
-                if (!__any_sync(0xffffffffu, e ? f1 : f0)) continue;
-                const float4 pa = e ? pa1 : pa0, qa = e ? qa1 : qa0;
-                settle_step(blk + e * teams, pa, qa);
-            }
-        }
-    }
-    if (blk < nblk) {
-        mine += VOTE_BLOCK;
-        const float4 pa = lds128(sp0 + blk * 512), qa = lds128(sq0 + blk * 512);
-        const bool f = fast_step(pa, qa);
-        if (__any_sync(0xffffffffu, f)) settle_step(blk, pa, qa);
-    }
-    int *counts = a.counts + ((size_t)b * a.K + k) * a.hn;
-#pragma unroll
-    for (int j = 0; j < NTW; ++j) {
-        int n0 = neg0[j], n1 = neg1[j];
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) { n0 += __shfl_xor_sync(0xffffffffu, n0, o); n1 += __shfl_xor_sync(0xffffffffu, n1, o); }
-        if (g == 0) {
-            const int h = hb + j * 8 + 2 * t;
-            if (h < a.hn && mine - n0) atomicAdd(counts + h, mine - n0);
-            if (h + 1 < a.hn && mine - n1) atomicAdd(counts + h + 1, mine - n1);
-        }
-    }
-}
-
-template <int NTW, int NWARP, int VOTE_TILE>
-constexpr size_t vote_mma_smem() { return (size_t)2 * (VOTE_TILE / VOTE_BLOCK) * 32 * 16 + (size_t)NWARP * 8 * NTW * 32 + 4 * NWARP * 4; }
-
 // Host side of the guard band (DESIGN.md "Guard band"), u = 2^-24:
 //   a test is re-evaluated exactly when |m| < band * S,  S = |hx-ox| + |hy-oy| + max_tile(|cx-ox|+|cy-oy|)
 //   band = 1.25 * u * (18 + 22*kappa + 9*G),  kappa = sqrt(1-t^2)/t,  G = 1/(t*sqrt(1-t^2)).
 // 2*(9+11*kappa)*u*S bounds twice the rounding error of m itself; 9*G*u*|h-c| is how far the reference's
 // fp32 cos can sit from the exact one, mapped into units of m; |h-c| <= S.  tools/band_check.c finds the
 // largest |m| of a fast/exact disagreement at 0.35x this bound (1e8 boundary samples).
-constexpr double MMA_EVAL = 16.0;
-
 ConeParams make_cone(float thresh)
 {
     ConeParams c;
@@ -595,25 +285,18 @@ ConeParams make_cone(float thresh)
         const double band = 1.25 * ldexp(1.0, -24) * (18.0 + 22.0 * kappa + 9.0 * G);
         c.kappa = (float)kappa;
         c.band = nextafterf((float)band, INFINITY);
-        // tensor path: the FFMA-chain rounding of m (part of the 18+22*kappa above) is replaced by the tf32x3 split
-        // (<= 3*2^-22 of every product) and the accumulation inside the MMA; MMA_EVAL bounds both per unit of
-        // (1+kappa)*S and is >= 2x the largest error tools/microbench3.cu measures on the GPU.
-        const double band_mma = 1.25 * ldexp(1.0, -24) * (18.0 + 22.0 * kappa + 9.0 * G + MMA_EVAL * (1.0 + kappa));
-        c.band_mma = nextafterf((float)band_mma, INFINITY);
     } else {
         c.kappa = 0.f;
         c.band = INFINITY;   // threshold outside (0,1): exact path for every test
-        c.band_mma = INFINITY;
     }
     return c;
 }
 
-// 0 / 1 -> FP32-pipe kernel, 512-pixel tile (the default); 2 / 3 -> same with a 256 / 1024-pixel tile;
-// 4 / 5 -> experimental tensor-path kernel (mma.sync tf32x3, 64 hypotheses per warp, 8 warps, 2 CTAs/SM) with a
-//          1024 / 512-pixel tile -- opt-in only, see launch_vote
-static int g_vote_variant = 0;
+// 0 / 1 -> 512-pixel tile (the default); 2 / 3 -> 256 / 1024-pixel tile (tooling: tools/tune_vote.py).  Results do not
+// depend on it.  Atomic: may be flipped while other host threads launch.
+static std::atomic<int> g_vote_variant{0};
 
-void set_vote_tuning(int variant) { g_vote_variant = variant; }
+void set_vote_tuning(int variant) { g_vote_variant.store(variant, std::memory_order_relaxed); }
 
 cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
 {
@@ -622,36 +305,7 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
     VoteK p;
     p.a = a;
     p.cone = make_cone(a.thresh);
-#define PVB_VOTE_MMA(NTW, NWARP, MINB, TILE)                                                                    \
-    do {                                                                                                    \
-        const int groups = (a.hn + 8 * (NTW) - 1) / (8 * (NTW));                                            \
-        int gpc = 1;                                                                                        \
-        while (gpc < groups && gpc < (NWARP)) gpc *= 2;                                                     \
-        const int chunks = (groups + gpc - 1) / gpc;                                                        \
-        dim3 g((a.cap + (TILE) - 1) / (TILE), a.K * chunks, a.B);                                           \
-        auto kern = vote_mma_kernel<NTW, NWARP, MINB, TILE>;                                                \
-        const size_t smem = vote_mma_smem<NTW, NWARP, TILE>();                                              \
-        static bool attr_done[64] = {};      /* per device: > 48 KB of dynamic shared memory is opt-in */    \
-        int dev = 0;                                                                                        \
-        e = cudaGetDevice(&dev);                                                                            \
-        if (e != cudaSuccess) return e;                                                                     \
-        if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                      \
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-            if (e != cudaSuccess) return e;                                                                 \
-            if (dev >= 0 && dev < 64) attr_done[dev] = true;                                                \
-        }                                                                                                   \
-        kern<<<g, (NWARP) * 32, smem, st>>>(p, gpc);                                                        \
-    } while (0)
-    // The tensor path is opt-in (variants 4/5): BASELINE.json's north star rules tensor cores out for this path, so the
-    // shipped default is the FP32-pipe kernel for every hn.  Measured for the record (profiles/r01_vote_tuning.md):
-    // 8-9 % faster at hn = 512 / 2048, 7 % slower at hn = 128.
-    const bool mma = g_vote_variant >= 4;
-    if (mma) {
-        if (g_vote_variant == 5) PVB_VOTE_MMA(8, 8, 2, 512);
-        else PVB_VOTE_MMA(8, 8, 2, 1024);
-        return cudaGetLastError();
-    }
-#undef PVB_VOTE_MMA
+    const int variant = g_vote_variant.load(std::memory_order_relaxed);
 #define PVB_VOTE(HPT, NT, MINB, TILE, WS)                                               \
     do {                                                                                \
         const int slices = (a.hn + (HPT) * (WS) * 32 - 1) / ((HPT) * (WS) * 32);        \
@@ -662,8 +316,8 @@ cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
     else if (a.hn <= 64) PVB_VOTE(2, 128, 8, 512, 1);
     else if (a.hn <= 128) PVB_VOTE(4, 128, 8, 512, 1);
     else if (a.hn <= 256) PVB_VOTE(4, 128, 8, 512, 2);
-    else if (g_vote_variant == 2) PVB_VOTE(4, 128, 8, 256, 4);
-    else if (g_vote_variant == 3) PVB_VOTE(4, 128, 8, 1024, 4);
+    else if (variant == 2) PVB_VOTE(4, 128, 8, 256, 4);
+    else if (variant == 3) PVB_VOTE(4, 128, 8, 1024, 4);
     else PVB_VOTE(4, 128, 8, 512, 4);     // best FP32-pipe shape on B200 (profiles/r01_vote_tuning.md)
 #undef PVB_VOTE
     return cudaGetLastError();
@@ -695,96 +349,119 @@ __device__ __forceinline__ bool vote_winner(float vx, float vy, float cx, float 
 }
 
 __global__ void __launch_bounds__(RF_THREADS)
-refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__restrict__ out, ConeParams cone)
+refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__restrict__ out, ConeParams cone, PeerPush pp)
 {
     const int split = blockIdx.x, k = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = RF_THREADS / 32;
     const int tn = min(a.tn[b], a.cap);
     const size_t bk = (size_t)b * a.K + k;
-    if (a.state[b] != 0 || tn <= 0) {   // :129-132 -> zeros
-        if (split == 0 && tid == 0) { out[bk * 2] = 0.f; out[bk * 2 + 1] = 0.f; win[bk] = make_float2(0.f, 0.f); }
-        return;
-    }
-    const int nsplit = (tn + RF_CHUNK - 1) / RF_CHUNK;   // CTAs that have pixels for this image
-    if (split >= nsplit) return;
-    // winner: every CTA of this (image,keypoint) finds it on its own (hn counts, L2-resident)
-    const int *counts = a.counts + bk * a.hn;
-    int bc = -1, bh = 0x7fffffff;
-    for (int h = tid; h < a.hn; h += RF_THREADS) {
-        const int c = counts[h];
-        if (c > bc) { bc = c; bh = h; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, o), oh = __shfl_xor_sync(0xffffffffu, bh, o);
-        if (oc > bc || (oc == bc && oh < bh)) { bc = oc; bh = oh; }
-    }
     __shared__ int s_c[NW], s_h[NW];
     __shared__ double s_acc[NW][5];
-    __shared__ int s_last;
-    if (lane == 0) { s_c[warp] = bc; s_h[warp] = bh; }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-        if (s_c[w] > bc || (s_c[w] == bc && s_h[w] < bh)) { bc = s_c[w]; bh = s_h[w]; }
-    // all_win_ratio starts at 0 and is replaced only by a strictly larger ratio (:165-167)
-    const float2 wpt = (bc > 0) ? a.hyp[bk * a.hn + bh] : make_float2(0.f, 0.f);
-    if (split == 0 && tid == 0) win[bk] = wpt;
-
-    const float2 *xy = a.xy + (size_t)b * a.cap;
-    const float2 *dk = a.dirs + bk * a.cap;
-    const int t_end = min(tn, (split + 1) * RF_CHUNK);
-    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
-    constexpr int RU = 4;     // loads in flight per thread (the loop is latency bound: 16 pixels per thread)
-    for (int t0 = split * RF_CHUNK + tid; t0 < t_end; t0 += RF_THREADS * RU) {
-        float2 v[RU], c[RU];
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            const int t = t0 + u * RF_THREADS;
-            v[u] = make_float2(0.f, 0.f); c[u] = make_float2(0.f, 0.f);
-            if (t < t_end) { v[u] = __ldg(dk + t); c[u] = __ldg(xy + t); }
+    __shared__ int s_last, s_final;
+    // Exactly one CTA per (image, keypoint) writes out[bk]: CTA 0 of a skipped image, otherwise the CTA that draws the
+    // last ticket.  Only those CTAs reach the exchange tail at the bottom.
+    if (a.state[b] != 0 || tn <= 0) {   // :129-132 -> zeros
+        if (split != 0) return;
+        if (tid == 0) { out[bk * 2] = 0.f; out[bk * 2 + 1] = 0.f; win[bk] = make_float2(0.f, 0.f); }
+    } else {
+        const int nsplit = (tn + RF_CHUNK - 1) / RF_CHUNK;   // CTAs that have pixels for this image
+        if (split >= nsplit) return;
+        // winner: every CTA of this (image,keypoint) finds it on its own (hn counts, L2-resident)
+        const int *counts = a.counts + bk * a.hn;
+        int bc = -1, bh = 0x7fffffff;
+        for (int h = tid; h < a.hn; h += RF_THREADS) {
+            const int c = counts[h];
+            if (c > bc) { bc = c; bh = h; }
         }
 #pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            if (t0 + u * RF_THREADS < t_end && vote_winner(v[u].x, v[u].y, c[u].x, c[u].y, wpt.x, wpt.y, cone)) {
-                const double nx = (double)v[u].y, ny = -(double)v[u].x;       // normal = (d_y, -d_x)  (:178-180)
-                const double bb = nx * (double)c[u].x + ny * (double)c[u].y;   // b = n . c             (:189)
-                a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;                // ATA                   (:190)
-                b0 += nx * bb; b1 += ny * bb;                                  // ATb                   (:191)
+        for (int o = 16; o > 0; o >>= 1) {
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o), oh = __shfl_xor_sync(0xffffffffu, bh, o);
+            if (oc > bc || (oc == bc && oh < bh)) { bc = oc; bh = oh; }
+        }
+        if (lane == 0) { s_c[warp] = bc; s_h[warp] = bh; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            if (s_c[w] > bc || (s_c[w] == bc && s_h[w] < bh)) { bc = s_c[w]; bh = s_h[w]; }
+        // all_win_ratio starts at 0 and is replaced only by a strictly larger ratio (:165-167)
+        const float2 wpt = (bc > 0) ? a.hyp[bk * a.hn + bh] : make_float2(0.f, 0.f);
+        if (split == 0 && tid == 0) win[bk] = wpt;
+
+        const float2 *xy = a.xy + (size_t)b * a.cap;
+        const float2 *dk = a.dirs + bk * a.cap;
+        const int t_end = min(tn, (split + 1) * RF_CHUNK);
+        double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
+        constexpr int RU = 4;     // loads in flight per thread (the loop is latency bound: 16 pixels per thread)
+        for (int t0 = split * RF_CHUNK + tid; t0 < t_end; t0 += RF_THREADS * RU) {
+            float2 v[RU], c[RU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const int t = t0 + u * RF_THREADS;
+                v[u] = make_float2(0.f, 0.f); c[u] = make_float2(0.f, 0.f);
+                if (t < t_end) { v[u] = __ldg(dk + t); c[u] = __ldg(xy + t); }
+            }
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                if (t0 + u * RF_THREADS < t_end && vote_winner(v[u].x, v[u].y, c[u].x, c[u].y, wpt.x, wpt.y, cone)) {
+                    const double nx = (double)v[u].y, ny = -(double)v[u].x;       // normal = (d_y, -d_x)  (:178-180)
+                    const double bb = nx * (double)c[u].x + ny * (double)c[u].y;   // b = n . c             (:189)
+                    a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;                // ATA                   (:190)
+                    b0 += nx * bb; b1 += ny * bb;                                  // ATb                   (:191)
+                }
             }
         }
-    }
-    a00 = warp_sum(a00); a01 = warp_sum(a01); a11 = warp_sum(a11); b0 = warp_sum(b0); b1 = warp_sum(b1);
-    if (lane == 0) { s_acc[warp][0] = a00; s_acc[warp][1] = a01; s_acc[warp][2] = a11; s_acc[warp][3] = b0; s_acc[warp][4] = b1; }
-    __syncthreads();
-    if (tid == 0) {
-        double *pp = rs.partial + (bk * rs.splits + split) * 5;
-        for (int i = 0; i < 5; ++i) {
-            double s = 0;
-            for (int w = 0; w < NW; ++w) s += s_acc[w][i];
-            __stcg(pp + i, s);
+        a00 = warp_sum(a00); a01 = warp_sum(a01); a11 = warp_sum(a11); b0 = warp_sum(b0); b1 = warp_sum(b1);
+        if (lane == 0) { s_acc[warp][0] = a00; s_acc[warp][1] = a01; s_acc[warp][2] = a11; s_acc[warp][3] = b0; s_acc[warp][4] = b1; }
+        __syncthreads();
+        if (tid == 0) {
+            double *pq = rs.partial + (bk * rs.splits + split) * 5;
+            for (int i = 0; i < 5; ++i) {
+                double s = 0;
+                for (int w = 0; w < NW; ++w) s += s_acc[w][i];
+                __stcg(pq + i, s);
+            }
+            __threadfence();
+            s_last = (atomicAdd(rs.ticket + bk, 1) == nsplit - 1);
         }
-        __threadfence();
-        s_last = (atomicAdd(rs.ticket + bk, 1) == nsplit - 1);
+        __syncthreads();
+        if (!s_last) return;
+        if (tid == 0) {
+            __threadfence();
+            double s[5] = {0, 0, 0, 0, 0};
+            for (int sp = 0; sp < nsplit; ++sp)            // fixed order -> deterministic sums
+                for (int i = 0; i < 5; ++i) s[i] += __ldcg(rs.partial + (bk * rs.splits + sp) * 5 + i);
+            const double det = s[0] * s[2] - s[1] * s[1];
+            float x, y;
+            if (det == 0.0 || !isfinite(det)) { x = (float)s[3]; y = (float)s[4]; }   // b_inv's identity fallback (:105-108)
+            else { x = (float)((s[2] * s[3] - s[1] * s[4]) / det); y = (float)((s[0] * s[4] - s[1] * s[3]) / det); }
+            out[bk * 2] = x; out[bk * 2 + 1] = y;
+        }
+    }
+    // ---- exchange tail (multi-GPU): the writer of the call's LAST result pushes the whole [B][K][2] block to every peer
+    if (pp.world <= 0) return;
+    if (tid == 0) {
+        __threadfence();                                                   // out[bk] before the arrival count
+        s_final = (atomicAdd(pp.done, 1) == a.B * a.K - 1);
     }
     __syncthreads();
-    if (!s_last || tid != 0) return;
-    __threadfence();
-    double s[5] = {0, 0, 0, 0, 0};
-    for (int sp = 0; sp < nsplit; ++sp)            // fixed order -> deterministic sums
-        for (int i = 0; i < 5; ++i) s[i] += __ldcg(rs.partial + (bk * rs.splits + sp) * 5 + i);
-    const double det = s[0] * s[2] - s[1] * s[1];
-    float x, y;
-    if (det == 0.0 || !isfinite(det)) { x = (float)s[3]; y = (float)s[4]; }   // b_inv's identity fallback (:105-108)
-    else { x = (float)((s[2] * s[3] - s[1] * s[4]) / det); y = (float)((s[0] * s[4] - s[1] * s[3]) / det); }
-    out[bk * 2] = x; out[bk * 2 + 1] = y;
+    if (!s_final) return;
+    __threadfence();                                                       // every other writer's out[] is visible now
+    for (int i = tid; i < pp.nfloats; i += RF_THREADS) {
+        const float v = __ldcg(out + i);
+        for (int r = 0; r < pp.world; ++r) pp.recv[r][i] = v;              // peer stores over NVLink (r == own rank: local)
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pp.world)                                                    // data first (fence above), then the flag
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[tid]), "l"(pp.seq) : "memory");
 }
 
-cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, cudaStream_t st)
+cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, const PeerPush &pp,
+                         cudaStream_t st)
 {
     dim3 g(rs.splits, a.K, a.B);
-    refit_kernel<<<g, RF_THREADS, 0, st>>>(a, win, rs, out_kpt, make_cone(a.thresh));
+    refit_kernel<<<g, RF_THREADS, 0, st>>>(a, win, rs, out_kpt, make_cone(a.thresh), pp);
     return cudaGetLastError();
 }
 

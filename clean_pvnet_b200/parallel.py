@@ -1,11 +1,31 @@
 """Multi-GPU use of the voting layer: one process per GPU, images sharded across ranks.
 
 The path is embarrassingly parallel over images: there is NO exchange inside the
-algorithm, so ranks run the single-GPU op on their contiguous slice of the batch and the only
-collective is an all_gather of the [B/G, K, 2] keypoints (+ [B/G, K, 2, 2] covariances) -- a few KB
-over NCCL/NVLink.  The philox sampling stream is keyed by the GLOBAL image index (`img_base`), so
-the gathered result is identical for any number of ranks.
+algorithm, so ranks run the single-GPU op on their contiguous slice of the batch and the only cross-GPU
+traffic is every rank's [B/G, K, 2] keypoints becoming visible on every rank -- a few KB.  The reference has
+nothing here (torch.nn.DataParallel in the trainer only, lib/train/trainers/trainer.py:5,11).
+The philox sampling stream is keyed by the GLOBAL image index (`img_base`), so the gathered result is
+identical for any number of ranks.
+
+Two ways to make the results visible:
+
+  gather="peer" (default on GPUs)   the exchange is FUSED INTO THE REFIT KERNEL: its last CTA stores the rank's block
+      straight into every peer's receive ring over NVLink and publishes a flag (csrc/exchange.cu, vote.cu "exchange
+      tail").  Nothing waits in the producing call and no collective kernel is launched; a tiny wait kernel, enqueued
+      `depth` calls later (or when the result is asked for), polls the rank's OWN memory and copies the slot out.
+      Round 1's per-call NCCL all_gather cost 0.30 ms of a 0.97 ms step at 8 GPUs (NCCL's kernel must become co-resident
+      on all GPUs and spins holding SM slots until the slowest rank arrives); this path has no such rendezvous.
+  gather="collective"               one torch.distributed all_gather per call (NCCL on GPUs, gloo in the CPU tests of the
+      host logic).  Kept as the portable fallback and as the baseline the fused path is measured against.
+
+Ring discipline of the peer path (what makes reuse of the receive slots safe without acknowledgements): the ring has
+2*depth slots; call s writes slot (s-1) % (2*depth) of every peer; the wait of call s-depth is always enqueued before
+call s is launched (ShardedVotingLayer does it).  A rank that executes call s has therefore finished its wait of call
+s-depth, which needed every peer's call s-depth to be complete, which -- stream order on the peer -- happened after the
+peer's wait of call s-2*depth: the slot call s overwrites has been copied out everywhere.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -20,9 +40,8 @@ def shard_bounds(total, world_size, rank):
 def all_gather_ragged(local, total, group=None, async_op=False):
     """all_gather of per-rank slices [n_r, ...] (n_r from shard_bounds) into [total, ...].
 
-    async_op=True returns (finish, work): the collective is enqueued on NCCL's own stream (after the producer of
-    `local` on the current stream) so it overlaps whatever the caller launches next; call `work.wait()` and then
-    `finish()` to get the gathered tensor."""
+    async_op=True returns (finish, work): the collective is enqueued on the backend's own stream (after the producer of
+    `local` on the current stream); call `work.wait()` and then `finish()` to get the gathered tensor."""
     world = dist.get_world_size(group)
     if world == 1:
         return (lambda: local, None) if async_op else local
@@ -42,21 +61,214 @@ def all_gather_ragged(local, total, group=None, async_op=False):
                                async_op=async_op)
 
     def finish():
-        if even:
-            return out
-        o = out.view(world, nmax, *local.shape[1:])
-        return torch.cat([o[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+        return _unpad(out, sizes, nmax, local.shape[1:])
 
     if async_op:
         return finish, work
     return finish()
 
 
+def _unpad(out, sizes, nmax, tail):
+    """[world*nmax, ...] with every rank's block padded to nmax rows -> [total, ...]."""
+    if all(hi - lo == nmax for lo, hi in sizes):
+        return out
+    o = out.view(len(sizes), nmax, *tail)
+    return torch.cat([o[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+class PeerExchange:
+    """A pvb_exchange (include/pvnet_vote_b200.h): this rank's receive ring, mapped into every peer through CUDA IPC.
+    Construction is collective over `group` (the 64-byte IPC handles travel through all_gather_object, once)."""
+
+    def __init__(self, bytes_per_rank, slots, group=None, device=None, rank=None, world=None):
+        from . import _lib
+        self._lib_mod = _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.slots = int(slots)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pvb_exchange_create(self.rank, self.world, self.slots, int(bytes_per_rank), ctypes.byref(h)))
+        self.handle = h
+        self.bytes_per_rank = int(self.lib.pvb_exchange_bytes_per_rank(h))
+
+    def connect_ipc(self):
+        """Collective: exchanges the IPC handles and maps every peer's ring."""
+        if self.world == 1:
+            return self
+        mine = ctypes.create_string_buffer(self._lib_mod.PVB_IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            self._lib_mod.check(self.lib.pvb_exchange_get_handle(self.handle, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=self.group)
+        blob = ctypes.create_string_buffer(b"".join(handles), self.world * self._lib_mod.PVB_IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            self._lib_mod.check(self.lib.pvb_exchange_connect(self.handle, blob))
+        return self
+
+    def connect_local(self, peers):
+        """Ranks that live in ONE process (tests, single-process multi-GPU): raw base pointers instead of IPC handles."""
+        arr = (ctypes.c_void_p * self.world)(*[self.lib.pvb_exchange_base(p.handle) for p in peers])
+        self._lib_mod.check(self.lib.pvb_exchange_connect_ptrs(self.handle, arr))
+        return self
+
+    def wait(self, seq, out, timeout_s=10.0):
+        """Enqueues the wait kernel of call `seq` on the current stream; `out` = uint8 [world*bytes_per_rank] on this device."""
+        self._lib_mod.check(self.lib.pvb_exchange_wait(self.handle, int(seq), out.data_ptr(), float(timeout_s),
+                                                       torch.cuda.current_stream(self.device).cuda_stream))
+
+    def check(self):
+        """Synchronises; raises if any wait timed out."""
+        self._lib_mod.check(self.lib.pvb_exchange_status(self.handle, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def close(self):
+        if self.handle:
+            with torch.cuda.device(self.device):
+                self.lib.pvb_exchange_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pending:
+    """Result of one sharded call: `.result()` returns the keypoints of the WHOLE batch, [total, K, 2], on this rank's
+    device (no host sync); `.local` is this rank's own slice, available at once."""
+
+    def __init__(self, owner, seq, local, sizes, nmax):
+        self._owner, self.seq, self.local, self._sizes, self._nmax = owner, seq, local, sizes, nmax
+        self._gathered = None
+        self._work = None
+        self._finish = None
+
+    def result(self):
+        if self._gathered is None:
+            self._owner._complete(self)
+        return self._gathered
+
+
+class ShardedVotingLayer:
+    """ransac_voting_layer_v3 over a batch sharded across the ranks of `group`.
+
+        layer = ShardedVotingLayer(total_images=128, K=17)           # collective (peer rings are mapped here)
+        p = layer(mask_local, vertex_local, 512, inlier_thresh=0.99, seed=s)   # launches; never blocks on a peer
+        kpt = p.result()                                             # [128, 17, 2] on every rank
+
+    Up to `depth` calls may be in flight before a result is asked for; the layer enqueues the wait of call s-depth itself
+    before launching call s (see the module docstring).  `op`/`gather="collective"` let the CPU tests drive the same
+    bookkeeping over gloo with a stand-in operator."""
+
+    def __init__(self, total_images, K, group=None, depth=4, gather="auto", device=None, op=None, timeout_s=10.0):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.total, self.K, self.depth = int(total_images), int(K), int(depth)
+        if self.depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.sizes = [shard_bounds(self.total, self.world, r) for r in range(self.world)]
+        self.nmax = max(hi - lo for lo, hi in self.sizes)
+        self.lo, self.hi = self.sizes[self.rank]
+        self.op = op
+        self.timeout_s = timeout_s
+        self.seq = 0
+        self.inflight = []          # Pending objects whose wait has not been enqueued yet, oldest first
+        self.exchange = None
+        self.gather_error = None
+        if gather not in ("auto", "peer", "collective"):
+            raise ValueError("gather must be 'auto', 'peer' or 'collective'")
+        use_peer = gather == "peer" or (gather == "auto" and op is None and torch.cuda.is_available())
+        if use_peer and min(hi - lo for lo, hi in self.sizes) == 0:
+            if gather == "peer":
+                raise ValueError("gather='peer' needs at least one image on every rank")
+            use_peer = False
+        if use_peer:
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+            ok = 1
+            try:
+                self.exchange = PeerExchange(self.nmax * self.K * 2 * 4, 2 * self.depth, group=group, device=self.device)
+                self.exchange.connect_ipc()
+            except Exception as e:          # no P2P between the GPUs, IPC unavailable, ...
+                self.gather_error = str(e)
+                ok = 0
+            # all ranks must agree on the path
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
+            if self.world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                if gather == "peer":
+                    raise RuntimeError(f"peer exchange unavailable: {self.gather_error or 'failed on another rank'}")
+                if self.exchange is not None:
+                    self.exchange.close()
+                self.exchange = None
+        self.mode = "peer" if self.exchange is not None else "collective"
+
+    def __call__(self, mask_local, vertex_local, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000, seed=0, **kw):
+        if mask_local.shape[0] != self.hi - self.lo:
+            raise ValueError("local batch does not match shard_bounds")
+        # ring discipline: the wait of call seq-depth goes onto the stream before call seq
+        while len(self.inflight) >= self.depth:
+            self._complete(self.inflight[0])
+        self.seq += 1
+        if self.exchange is not None:
+            from .ransac_voting_gpu import ransac_voting_layer_v3
+            local = ransac_voting_layer_v3(mask_local, vertex_local, round_hyp_num, inlier_thresh=inlier_thresh,
+                                           min_num=min_num, max_num=max_num, seed=seed, img_base=self.lo,
+                                           _exchange=(self.exchange.handle, self.seq), **kw)
+            p = Pending(self, self.seq, local, self.sizes, self.nmax)
+        else:
+            op = self.op
+            if op is None:
+                from .ransac_voting_gpu import ransac_voting_layer_v3 as op
+            local = op(mask_local, vertex_local, round_hyp_num, inlier_thresh=inlier_thresh, min_num=min_num,
+                       max_num=max_num, seed=seed, img_base=self.lo, **kw)
+            p = Pending(self, self.seq, local, self.sizes, self.nmax)
+            p._finish, p._work = all_gather_ragged(local, self.total, self.group, async_op=True)
+        self.inflight.append(p)
+        return p
+
+    def _complete(self, p):
+        """Enqueue whatever makes p's gathered tensor valid on the current stream (in call order: older calls first)."""
+        while self.inflight and self.inflight[0].seq <= p.seq:
+            q = self.inflight.pop(0)
+            if self.exchange is not None:
+                buf = torch.empty(self.world * self.exchange.bytes_per_rank, dtype=torch.uint8, device=self.device)
+                self.exchange.wait(q.seq, buf, self.timeout_s)
+                rows = buf.view(self.world, self.exchange.bytes_per_rank)[:, : self.nmax * self.K * 8]
+                out = rows.reshape(self.world * self.nmax * self.K * 8).view(torch.float32).view(self.world * self.nmax, self.K, 2)
+                q._gathered = _unpad(out, self.sizes, self.nmax, (self.K, 2))
+            else:
+                if q._work is not None:
+                    q._work.wait()
+                q._gathered = q._finish()
+
+    def drain(self):
+        """Enqueue the waits of everything still in flight (no host sync)."""
+        if self.inflight:
+            self._complete(self.inflight[-1])
+
+    def check(self):
+        """Host sync + error check of the peer path (a timed-out wait fills its result with NaN and raises here)."""
+        self.drain()
+        if self.exchange is not None:
+            self.exchange.check()
+
+    def close(self):
+        if self.exchange is not None:
+            self.exchange.close()
+            self.exchange = None
+
+
 def sharded_ransac_voting_layer_v3(mask_local, vertex_local, round_hyp_num, total_images, inlier_thresh=0.999,
                                    min_num=5, max_num=30000, seed=0, group=None, op=None):
-    """Runs ransac_voting_layer_v3 on this rank's images (a shard_bounds slice of a `total_images`
-    batch) and returns the keypoints of the WHOLE batch on every rank.  `op` defaults to the CUDA
-    operator; tests inject a stand-in to exercise the sharding logic on CPU/gloo."""
+    """One-shot form: runs ransac_voting_layer_v3 on this rank's images (a shard_bounds slice of a `total_images`
+    batch) and returns the keypoints of the WHOLE batch on every rank through one collective.  For repeated calls use
+    ShardedVotingLayer (peer-memory exchange, no collective in the steady state).  `op` defaults to the CUDA operator;
+    tests inject a stand-in to exercise the sharding logic on CPU/gloo."""
     if op is None:
         from .ransac_voting_gpu import ransac_voting_layer_v3 as op
     rank, world = dist.get_rank(group), dist.get_world_size(group)

@@ -160,7 +160,7 @@ def _prep_optional(t, shape, dtype, name, device):
 
 
 def _run(op, mask, vertex, hn, inlier_thresh, min_num, max_num, mean=None, idxs=None, selection=None,
-         rng="philox", seed=None, img_base=0, capacity=None, debug=False, rounds=1, round_hn=None):
+         rng="philox", seed=None, img_base=0, capacity=None, debug=False, rounds=1, round_hn=None, exchange=None):
     mask, vertex = _check_inputs(mask, vertex)
     lib = _lib.load()
     dev = vertex.device
@@ -179,6 +179,11 @@ def _run(op, mask, vertex, hn, inlier_thresh, min_num, max_num, mean=None, idxs=
             seed = _draw_seed() if (idxs is None or selection is None) else 0
         if capacity is None and selection is not None:
             capacity = H * W
+        if capacity is not None:
+            # a too-small capacity would silently truncate the pixel set (the kernels clamp tn): refuse it up front
+            need = H * W if selection is not None else min(H * W, int(max_num + 8 * math.sqrt(max(max_num, 0)) + 64))
+            if int(capacity) < need:
+                raise ValueError(f"capacity={capacity} cannot hold the selection (needs >= {need}; H*W is always safe)")
         d = _make_desc(mask, vertex, hn, inlier_thresh, min_num, max_num, select_mode, seed, img_base, capacity)
         nbytes = lib.pvb_workspace_bytes(d)
         if nbytes == 0:
@@ -189,7 +194,10 @@ def _run(op, mask, vertex, hn, inlier_thresh, min_num, max_num, mean=None, idxs=
         sp = selection.data_ptr() if selection is not None else None
         if op == "v3":
             out = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
-            if B:
+            if exchange is not None:          # (handle, seq): the refit kernel also pushes `out` to every peer
+                _lib.check(lib.pvb_ransac_voting_v3_push(d, mask.data_ptr(), vertex.data_ptr(), ip, sp, out.data_ptr(),
+                                                         ws.data_ptr(), ws.numel(), exchange[0], exchange[1], stream))
+            elif B:
                 _lib.check(lib.pvb_ransac_voting_v3(d, mask.data_ptr(), vertex.data_ptr(), ip, sp, out.data_ptr(),
                                                     ws.data_ptr(), ws.numel(), stream))
         else:
@@ -212,7 +220,7 @@ def _run(op, mask, vertex, hn, inlier_thresh, min_num, max_num, mean=None, idxs=
 
 def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
                            min_num=5, max_num=30000, *, idxs=None, selection=None, rng="philox", seed=None,
-                           img_base=0, capacity=None, debug=False):
+                           img_base=0, capacity=None, debug=False, _exchange=None):
     """Drop-in for ransac_voting_gpu.py:112-199.
 
     :param mask:      [b,h,w]   any integer / bool / float dtype, any strides
@@ -227,7 +235,8 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
     """
     del confidence, max_iter
     return _run("v3", mask, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num, idxs=idxs,
-                selection=selection, rng=rng, seed=seed, img_base=img_base, capacity=capacity, debug=debug)
+                selection=selection, rng=rng, seed=seed, img_base=img_base, capacity=capacity, debug=debug,
+                exchange=_exchange)
 
 
 def ransac_voting_layer(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
@@ -265,12 +274,15 @@ _host_scratch = {}
 
 def ransac_voting_layer_v3_host(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
                                 min_num=5, max_num=30000, *, device=None, chunk_images=2, seed=None, img_base=0,
-                                out=None, zero_copy=True):
+                                out=None, mode="auto"):
     """ransac_voting_layer_v3 for HOST tensors: the C ABI's host-buffer entry (pvb_ransac_voting_v3_host)
-    processes the batch in `chunk_images`-sized pieces on two streams and writes keypoints to a host tensor.
-    With pinned inputs and zero_copy=True (default) the kernels read the inputs in place over PCIe: the mask
-    is streamed once and only the selected pixels' vertex rows cross the bus (tn*K*8 bytes per image instead
-    of the dense H*W*K*8).  Pageable inputs or zero_copy=False use staged cudaMemcpyAsync copies."""
+    processes the batch in `chunk_images`-sized pieces on three streams and writes keypoints to a host tensor.
+    mode (what crosses PCIe, see include/pvnet_vote_b200.h):
+        "auto"     pinned inputs: the mask goes by DMA (one cudaMemcpyAsync per piece), the vertex field is read in place and
+                   only the selected pixels' rows cross the bus (tn*K*8 bytes per image instead of the dense H*W*K*8);
+                   pageable inputs are staged
+        "inplace"  both tensors read in place by the kernels (no DMA)
+        "staged"   both tensors copied with cudaMemcpyAsync"""
     del confidence, max_iter
     if mask.is_cuda or vertex.is_cuda:
         raise RuntimeError("ransac_voting_layer_v3_host takes host tensors")
@@ -297,8 +309,8 @@ def ransac_voting_layer_v3_host(mask, vertex, round_hyp_num, inlier_thresh=0.999
         if sc is None or sc.numel() < nbytes:
             sc = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             _host_scratch[key] = sc
-        _lib.check(lib.pvb_set_host_mode(1 if zero_copy else 0))
-        _lib.check(lib.pvb_ransac_voting_v3_host(d, mask.data_ptr(), vertex.data_ptr(), out.data_ptr(), chunk,
+        flags = {"auto": 0, "inplace": _lib.PVB_HOST_INPLACE_MASK, "staged": _lib.PVB_HOST_STAGE_VERTEX}[mode]
+        _lib.check(lib.pvb_ransac_voting_v3_host(d, mask.data_ptr(), vertex.data_ptr(), out.data_ptr(), chunk, flags,
                                                  sc.data_ptr(), sc.numel(),
                                                  torch.cuda.current_stream(dev).cuda_stream))
     return out

@@ -25,8 +25,9 @@
  *   - plain C: device pointers, sizes, strides (in ELEMENTS), a CUDA stream
  *     handle.  No torch types.  All work is enqueued on `stream`; no entry
  *     point synchronises or allocates (the caller owns the workspace), so the
- *     calls are CUDA-graph capturable.  Exception: the *_host variants, which
- *     take HOST buffers and run their own copy/compute pipeline.
+ *     calls are CUDA-graph capturable.  Exceptions: the *_host variants, which
+ *     take HOST buffers and run their own copy/compute pipeline, and the setup
+ *     calls of pvb_exchange (create / connect / destroy).
  *   - every function returns PVB_OK (0) or a pvb_status error code;
  *     pvb_last_error() returns a thread-local description.  Nothing calls
  *     exit()/abort() (the reference's gpuErrchk does, cuda_common.h:19-25).
@@ -43,7 +44,7 @@
 extern "C" {
 #endif
 
-#define PVB_VERSION 100
+#define PVB_VERSION 200
 
 #if defined(__GNUC__)
 #define PVB_API __attribute__((visibility("default")))
@@ -58,7 +59,8 @@ typedef enum pvb_status {
     PVB_ERR_INVALID = 1,   /* bad argument (null pointer, shape, dtype, stride) */
     PVB_ERR_CUDA = 2,      /* CUDA runtime / launch failure, or no usable device */
     PVB_ERR_WORKSPACE = 3, /* workspace too small or misaligned */
-    PVB_ERR_CAPACITY = 4   /* more pixels selected than `capacity` (reported by pvb_read_status) */
+    PVB_ERR_CAPACITY = 4,  /* more pixels selected than `capacity` (reported by pvb_read_status) */
+    PVB_ERR_TIMEOUT = 5    /* pvb_exchange_wait gave up: a rank never published its result */
 } pvb_status;
 
 /* element type of the mask tensor (reference: any dtype goes through .byte(), ransac_voting_gpu.py:125) */
@@ -116,6 +118,7 @@ typedef struct pvb_layout {
     size_t win;      /* float2[B][K] winning hypothesis before the refit */
     size_t refit_partial; /* double[B][K][refit_splits][5] partial normal equations */
     size_t refit_ticket;  /* int32[B][K] arrival counters of the refit CTAs */
+    size_t refit_done;    /* int32 (image,keypoint) results written (multi-GPU push trigger) */
     int32_t nwords;  /* ceil(H*W/32) */
     int32_t nblocks; /* ceil(nwords/128) */
     int32_t capacity;
@@ -203,21 +206,51 @@ PVB_API int pvb_read_status(const pvb_desc *d, const void *workspace, pvb_stream
 
 /* HOST-buffer variant of pvb_ransac_voting_v3: mask/vertex/out_kpt are host pointers
  * (pinned for full speed), contiguous [B,H,W] / [B,H,W,K,2] / [B,K,2].  Splits the batch into
- * `chunk_images`-sized pieces on two internal streams so that one piece's PCIe traffic overlaps the other's
- * kernels; see pvb_set_host_mode for what crosses the bus.
+ * `chunk_images`-sized pieces on three internal streams so that one piece's PCIe traffic overlaps the others'
+ * kernels.  What crosses the bus is chosen per call by `flags`:
+ *   0 (default)            the mask is staged -- one contiguous cudaMemcpyAsync per piece, the copy engine's PCIe
+ *                          rate -- and the vertex field is read IN PLACE from the pinned host tensor: gather fetches only the
+ *                          SELECTED pixels' rows (tn*K*8 bytes per image instead of the dense H*W*K*8)
+ *   PVB_HOST_STAGE_VERTEX  also copy the dense vertex field (pageable inputs are always staged)
+ *   PVB_HOST_INPLACE_MASK  read the mask in place as well (no DMA at all; round 1's mode)
  * Stream-ordered after the work already queued on `stream`; `stream` is synchronised before the
  * call returns (the result is in host memory), so CUDA events recorded on `stream` around the call
  * bracket all copies and kernels.  dev_scratch: 256-byte aligned device memory of
- * pvb_host_scratch_bytes(d, chunk_images) bytes. */
+ * pvb_host_scratch_bytes(d, chunk_images) bytes.  Thread-safe (per-thread, per-device streams). */
+#define PVB_HOST_STAGE_VERTEX 2u
+#define PVB_HOST_INPLACE_MASK 4u
 PVB_API size_t pvb_host_scratch_bytes(const pvb_desc *d, int32_t chunk_images);
-/* How the host entry moves its inputs (process-wide).  zero_copy != 0 (default): when mask_host and vertex_host
- * are pinned, device-mapped host memory the kernels read them in place over PCIe -- the mask is streamed once and
- * only the SELECTED pixels' vertex rows are fetched (tn*K*8 bytes per image instead of H*W*K*8).  Pageable
- * inputs, or zero_copy == 0, take the staged path (cudaMemcpyAsync of both tensors, chunk by chunk). */
-PVB_API int pvb_set_host_mode(int32_t zero_copy);
 PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, const float *vertex_host,
-                              float *out_kpt_host, int32_t chunk_images,
+                              float *out_kpt_host, int32_t chunk_images, uint32_t flags,
                               void *dev_scratch, size_t dev_scratch_bytes, pvb_stream_t stream);
+
+/* ---- multi-GPU: images are sharded across ranks, one process per GPU --------------------------------
+ * The path has no exchange inside the algorithm; what crosses GPUs is each rank's [B_r,K,2] keypoints becoming visible on
+ * every rank.  The reference has no counterpart (torch.nn.DataParallel in the trainer only, lib/train/trainers/trainer.py:11).
+ * A pvb_exchange is a receive ring in this rank's HBM -- recv[slots][world][bytes_per_rank] + one flag word per
+ * (slot, rank) -- mapped into every peer through CUDA IPC.  pvb_ransac_voting_v3_push is pvb_ransac_voting_v3 whose refit
+ * kernel ALSO stores the rank's result block into slot (seq-1)%slots of every peer's ring over NVLink and then publishes
+ * `seq` in the peers' flag words; it never waits.  pvb_exchange_wait enqueues a one-CTA kernel that polls this rank's own
+ * flags until all `world` ranks have published `seq` (bounded by timeout_s) and copies the slot to `out`
+ * (device, [world][bytes_per_rank], 16-byte aligned).  Ring discipline (caller): before call `seq` is launched, the wait of
+ * call `seq - slots/2` must already be enqueued on the same stream on every rank; seq starts at 1 and increases by 1 per
+ * call on every rank alike.  Setup (once): create -> get_handle -> all-gather the 64-byte handles by any means (e.g.
+ * torch.distributed.all_gather_object) -> connect.  connect_ptrs takes raw base pointers instead (ranks that live in one
+ * process, or memory mapped by other means). */
+typedef struct pvb_exchange pvb_exchange;
+#define PVB_IPC_HANDLE_BYTES 64
+PVB_API int pvb_exchange_create(int32_t rank, int32_t world, int32_t slots, size_t bytes_per_rank, pvb_exchange **out);
+PVB_API size_t pvb_exchange_bytes_per_rank(const pvb_exchange *ex); /* bytes_per_rank rounded up to 16 */
+PVB_API void *pvb_exchange_base(const pvb_exchange *ex);
+PVB_API int pvb_exchange_get_handle(const pvb_exchange *ex, void *handle /* PVB_IPC_HANDLE_BYTES */);
+PVB_API int pvb_exchange_connect(pvb_exchange *ex, const void *handles /* world * PVB_IPC_HANDLE_BYTES, rank order */);
+PVB_API int pvb_exchange_connect_ptrs(pvb_exchange *ex, void *const *bases /* world base pointers, rank order */);
+PVB_API int pvb_ransac_voting_v3_push(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
+                                      const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
+                                      pvb_exchange *exchange, uint64_t seq, pvb_stream_t stream);
+PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, double timeout_s, pvb_stream_t stream);
+PVB_API int pvb_exchange_status(pvb_exchange *ex, pvb_stream_t stream); /* synchronises; PVB_ERR_TIMEOUT after a timed-out wait */
+PVB_API int pvb_exchange_destroy(pvb_exchange *ex);
 
 /* Stage timing (tooling, used by bench.py).  When enabled, the layer entry points record CUDA
  * events on the launching stream around each stage; pvb_profile_read() synchronises those events
@@ -229,11 +262,8 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_FINISH = 3,   /* winner + refit, or covariance */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
-/* Tuning switch (tooling; process-wide).  reserved: pass 0.  vote_variant selects the vote kernel:
- * 0 = default = 1 = FP32-pipe kernel with a 512-pixel tile; 2 / 3 = the same with a 256 / 1024-pixel tile;
- * 4 / 5 = experimental tensor-path kernel (mma.sync, tf32 x 3 split) with a 1024 / 512-pixel tile -- opt-in only: the
- * path's specification excludes tensor cores, the variant exists to document what they would buy.
- * Results do not depend on the variant (every one reproduces the reference's inlier counts). */
+/* Tuning switch (tooling; process-wide, atomic).  reserved: pass 0.  vote_variant selects the pixel tile of the vote
+ * kernel: 0 = 1 = 512 pixels (default), 2 = 256, 3 = 1024.  Results do not depend on it. */
 PVB_API int pvb_set_tuning(int32_t reserved, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);
 PVB_API int pvb_profile_read(double *ms, int32_t n);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(pvb):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pvnet_vote_b200.h but not exported"
     assert set(names) == set(pvb._lib.SIGNATURES), "ctypes table and header disagree"
-    assert pvb._lib.load().pvb_version() == 100
+    assert pvb._lib.load().pvb_version() == 200
 
 
 def _desc(pvb, **kw):

@@ -46,6 +46,55 @@ def _worker(rank, world, port, total, q):
         dist.destroy_process_group()
 
 
+def _layer_worker(rank, world, port, total, steps, depth, q):
+    """ShardedVotingLayer over gloo: `steps` pipelined calls with at most `depth` in flight, results asked for out of
+    order -- the same bookkeeping (sequence numbers, deferred completion, ragged un-padding) the peer path uses on GPUs."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clean_pvnet_b200 import parallel, synth
+        mask, vertex, _ = synth.make_inputs("tiny", device="cpu", seed=78, B=total)
+        lo, hi = parallel.shard_bounds(total, world, rank)
+        layer = parallel.ShardedVotingLayer(total, vertex.shape[3], depth=depth, gather="collective", op=_oracle_op)
+        assert layer.mode == "collective"
+        pend = [layer(mask[lo:hi], vertex[lo:hi], 16, inlier_thresh=0.99, max_num=300, seed=100 + s) for s in range(steps)]
+        assert len(layer.inflight) <= depth                    # older calls were completed by the layer itself
+        assert [p.seq for p in pend] == list(range(1, steps + 1))
+        outs = [None] * steps
+        for s in reversed(range(steps)):                       # out of order on purpose
+            outs[s] = pend[s].result().numpy()
+        layer.check()
+        assert not layer.inflight
+        assert np.array_equal(pend[0].local.numpy(), outs[0][lo:hi])
+        if rank == 0:
+            q.put(np.stack(outs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("total,depth", [(5, 2), (4, 4)])
+def test_sharded_layer_pipelined_calls(total, depth):
+    steps = 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_layer_worker, args=(r, 2, port, total, steps, depth, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from clean_pvnet_b200 import synth
+    mask, vertex, _ = synth.make_inputs("tiny", device="cpu", seed=78, B=total)
+    for s in range(steps):
+        want = _oracle_op(mask, vertex, 16, inlier_thresh=0.99, max_num=300, seed=100 + s).numpy()
+        assert np.array_equal(got[s], want), s
+
+
 def test_shard_bounds():
     from clean_pvnet_b200.parallel import shard_bounds
     for total in (0, 1, 5, 16, 128, 131):

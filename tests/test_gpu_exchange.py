@@ -1,0 +1,100 @@
+"""GPU: the multi-GPU result exchange (pvb_exchange, csrc/exchange.cu + the refit kernel's exchange tail) on ONE device.
+
+Two (or three) "ranks" live in this process, each with its own receive ring in HBM; the rings are connected by raw base
+pointers (pvb_exchange_connect_ptrs) instead of CUDA IPC handles, everything else -- the peer stores from the refit
+kernel, the flags, the wait kernel, the ring schedule -- is the code that runs across GPUs.  bench.py --gpus N asserts the
+same equality across real NVLink peers ("gather_check")."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(pvb, world, nmax, K, depth):
+    from clean_pvnet_b200 import parallel
+    exs = [parallel.PeerExchange(nmax * K * 8, 2 * depth, rank=r, world=world, device="cuda:0") for r in range(world)]
+    for e in exs:
+        e.connect_local(exs)
+    return exs
+
+
+def _gathered(ex, seq, world, nmax, K, sizes):
+    from clean_pvnet_b200 import parallel
+    buf = torch.empty(world * ex.bytes_per_rank, dtype=torch.uint8, device="cuda:0")
+    ex.wait(seq, buf, timeout_s=5.0)
+    rows = buf.view(world, ex.bytes_per_rank)[:, : nmax * K * 8]
+    out = rows.reshape(-1).view(torch.float32).view(world * nmax, K, 2)
+    return parallel._unpad(out, sizes, nmax, (K, 2))
+
+
+@pytest.mark.parametrize("world,total", [(2, 6), (3, 7)])
+def test_pushed_results_equal_the_single_gpu_result(pvb, world, total):
+    from clean_pvnet_b200 import parallel, synth
+    mask, vertex, _ = synth.make_inputs("small", device="cuda:0", seed=31, B=total)
+    K = vertex.shape[3]
+    sizes = [parallel.shard_bounds(total, world, r) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in sizes)
+    depth = 2
+    exs = _make(pvb, world, nmax, K, depth)
+    try:
+        steps = 7                                   # > 2*depth: every slot of the ring is reused
+        pending = []
+        for s in range(1, steps + 1):
+            if s > depth:                           # ring discipline: wait of call s-depth before call s, on every rank
+                seq0 = s - depth
+                want = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, seed=500 + seq0, max_num=700)
+                for r in range(world):
+                    got = _gathered(exs[r], seq0, world, nmax, K, sizes)
+                    assert torch.equal(got, want), (seq0, r)
+                pending.remove(seq0)
+            for r, (lo, hi) in enumerate(sizes):
+                local = pvb.ransac_voting_layer_v3(mask[lo:hi], vertex[lo:hi], 64, inlier_thresh=0.99, seed=500 + s, max_num=700,
+                                                   img_base=lo, _exchange=(exs[r].handle, s))
+                assert local.shape == (hi - lo, K, 2)
+            pending.append(s)
+        for seq0 in pending:
+            want = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, seed=500 + seq0, max_num=700)
+            for r in range(world):
+                assert torch.equal(_gathered(exs[r], seq0, world, nmax, K, sizes), want), (seq0, r)
+        for e in exs:
+            e.check()
+    finally:
+        for e in exs:
+            e.close()
+
+
+def test_wait_times_out_instead_of_hanging(pvb):
+    """A rank that never publishes: the wait kernel gives up after timeout_s, poisons its output and the status call raises."""
+    from clean_pvnet_b200 import synth
+    mask, vertex, _ = synth.make_inputs("small", device="cuda:0", seed=32, B=2)
+    K = vertex.shape[3]
+    exs = _make(pvb, 2, 1, K, 2)
+    try:
+        pvb.ransac_voting_layer_v3(mask[:1], vertex[:1], 64, inlier_thresh=0.99, seed=1, max_num=700, _exchange=(exs[0].handle, 1))
+        buf = torch.zeros(2 * exs[0].bytes_per_rank, dtype=torch.uint8, device="cuda:0")
+        exs[0].wait(1, buf, timeout_s=0.2)          # rank 1 never ran call 1
+        torch.cuda.synchronize()
+        assert torch.isnan(buf.view(torch.float32)).all()
+        with pytest.raises(RuntimeError, match="timed out"):
+            exs[0].check()
+    finally:
+        for e in exs:
+            e.close()
+
+
+def test_argument_checks(pvb):
+    from clean_pvnet_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.pvb_exchange_create(2, 2, 4, 64, ctypes.byref(h)) == _lib.PVB_ERR_INVALID      # rank out of range
+    assert lib.pvb_exchange_create(0, 2, 1, 64, ctypes.byref(h)) == _lib.PVB_ERR_INVALID      # slots < 2
+    _lib.check(lib.pvb_exchange_create(0, 2, 4, 64, ctypes.byref(h)))
+    try:
+        from clean_pvnet_b200 import synth
+        mask, vertex, _ = synth.make_inputs("small", device="cuda:0", seed=33, B=1)
+        with pytest.raises(RuntimeError, match="not connected"):
+            pvb.ransac_voting_layer_v3(mask, vertex, 64, _exchange=(h, 1))
+    finally:
+        lib.pvb_exchange_destroy(h)

@@ -279,9 +279,9 @@ def test_host_buffer_entry_matches_device_entry(pvb):
     dev = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, seed=21, max_num=700)
     mh, vh = mask.cpu().pin_memory(), vertex.cpu().pin_memory()
     for chunk in (1, 2, 5):
-        for zero_copy in (True, False):       # in-place PCIe reads of the pinned tensors / staged copies
+        for mode in ("auto", "inplace", "staged"):   # mask by DMA + vertex rows in place / all in place / all copied
             host = pvb.ransac_voting_layer_v3_host(mh, vh, 64, inlier_thresh=0.99, seed=21, max_num=700,
-                                                   chunk_images=chunk, zero_copy=zero_copy)
+                                                   chunk_images=chunk, mode=mode)
             assert not host.is_cuda
             assert torch.equal(host, dev.cpu())
     # pageable (unpinned) inputs silently take the staged path

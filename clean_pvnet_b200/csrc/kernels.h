@@ -14,7 +14,7 @@ struct SelectArgs {
     long long vs[5];              // vertex strides (elements)
     const float *selection;       // optional [B,H,W]
     int B, H, W, K, nwords, nblocks, cap, min_num, max_num, img_base;
-    int rowwise_gather;           // 1: vertex is zero-copy host memory, read whole pixel rows per warp
+    int rowwise_gather;           // 1: vertex is read in place from pinned host memory: always whole pixel rows per warp
     int seg_classes;              // > 0: `mask` points to fp32 logits [B,C,H,W]; the mask is argmax over C
     long long seg_cs;             // class stride of the logits (elements)
     long long *mask_out;          // optional int64 [B,H,W] argmax output
@@ -47,6 +47,7 @@ cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st);
 // counts[b][k][h] = #pixels voting for hyp[b][k][h]   (zeroes counts itself)
 cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st);
 void set_vote_tuning(int variant);   // tooling: pixel-tile size per CTA
+void set_gather_tuning(int mode);    // tooling: gather access pattern (select.cu)
 // argmax + winner refit -> out_kpt [B][K][2], win [B][K].  The pixels of one (image,keypoint) are split
 // over `splits` CTAs; partial normal equations meet in `partial`, the last CTA to arrive (ticket) adds
 // them in a fixed order and solves, so the result is deterministic.

@@ -15,6 +15,7 @@
 // All three kernels are HBM/latency bound: the mask is read exactly once (mask_bits), the
 // bitmap (1/256 of an int64 mask) is what later passes touch, and the vertex field is read
 // only at selected pixels.
+#include <atomic>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,17 +30,26 @@ __device__ __forceinline__ uint32_t mask_byte<double>(double v) { return (uint32
 
 constexpr int MB_WARPS = 8;
 constexpr int MB_UNROLL = 8;
-constexpr int MB_WORDS = 16;     // bitmap words (of 32 pixels) per warp: 2 rounds of 8 loads in flight per lane
+constexpr int MB_WORDS = 16;     // bitmap words (of 32 pixels) per warp
 
-// One warp converts 512 pixels into 16 bitmap words with coalesced loads (lane = pixel within
-// word) and ballots; lane i keeps word i so the words leave as one coalesced store.  Loads are
-// issued MB_UNROLL at a time before any ballot so that each warp keeps 2 KB (int64 masks) in flight;
-// 16 words per warp gives a full wave of 64 resident warps per SM at 480x640 x 16 images.
+// One warp converts 512 pixels into 16 bitmap words; lane i keeps word i so the words leave as one coalesced store.
+//   VEC path (contiguous image, 16-byte aligned, all 512 pixels in range): every lane loads 16 BYTES per instruction
+//   (E = 16/sizeof(T) consecutive pixels: 2 for the int64 mask torch.argmax produces), all loads of the warp's span are
+//   issued before the first use -- 4 KB in flight per warp for int64 -- and the E-bit pieces of the 32/E lanes that
+//   share a bitmap word are OR-reduced with one REDUX per load instruction.
+//   Scalar path (strided masks, image tail): one pixel per lane and load, MB_UNROLL loads in flight, ballots.
+template <typename T, int MODE>
+__device__ __forceinline__ void mask_pred(T v, bool &sel, uint32_t &val)
+{
+    if (MODE == PVB_SELECT_BYTE) { val = mask_byte<T>(v); sel = val != 0; }
+    else { sel = (v == (T)1); val = sel; }
+}
+
 template <typename T, int MODE, bool CONTIG>
 __global__ void __launch_bounds__(MB_WARPS * 32)
 mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long long sx, int H, int W,
                  int nwords, uint32_t *__restrict__ bits, unsigned long long *__restrict__ fgsum,
-                 int *__restrict__ nz)
+                 int *__restrict__ nz, int vec_ok)
 {
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -47,37 +57,62 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
     if (w0 >= nwords) return;
     const int HW = H * W;
     const T *mb = mask + (long long)b * sb;
-    // fast path: contiguous image and all MB_WORDS*32 pixels of this warp in range -> no per-element address
-    // arithmetic or bounds test between the loads
     const bool full = CONTIG && ((w0 + MB_WORDS) * 32 <= HW);
     uint32_t myword = 0, sum = 0;
-    for (int i0 = 0; i0 < MB_WORDS; i0 += MB_UNROLL) {
-        T v[MB_UNROLL];
-        if (full) {
-            const T *q = mb + (size_t)(w0 + i0) * 32 + lane;
+    if (full && vec_ok) {
+        constexpr int E = 16 / (int)sizeof(T);            // pixels per lane and load
+        constexpr int NL = MB_WORDS / E;                  // load instructions per warp (E words each)
+        constexpr int LPW = 32 / E;                       // lanes that share one bitmap word
+        union V { uint4 u; T t[E]; };
+        V v[NL];
+        const uint4 *q = reinterpret_cast<const uint4 *>(mb + (size_t)w0 * 32) + lane;
 #pragma unroll
-            for (int u = 0; u < MB_UNROLL; ++u) v[u] = __ldg(q + u * 32);
-        } else {
+        for (int u = 0; u < NL; ++u) v[u].u = __ldg(q + u * 32);
+        const int grp = lane / LPW;                       // word (within the load) this lane contributes to
+        const uint32_t gmask = (LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u)) << (grp * LPW);
 #pragma unroll
-            for (int u = 0; u < MB_UNROLL; ++u) {
-                const int p = (w0 + i0 + u) * 32 + lane;
-                v[u] = (T)0;
-                if (p < HW) {
-                    long long off = p;
-                    if (!CONTIG) { const int y = p / W; off = (long long)y * sy + (long long)(p - y * W) * sx; }
-                    v[u] = __ldg(mb + off);
+        for (int u = 0; u < NL; ++u) {
+            uint32_t lb = 0;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                bool sel; uint32_t val;
+                mask_pred<T, MODE>(v[u].t[j], sel, val);
+                lb |= (sel ? 1u : 0u) << j;
+                sum += val;
+            }
+            const uint32_t word = __reduce_or_sync(gmask, lb << ((lane % LPW) * E));
+            // word (u*E + g) was assembled by group g; lane (u*E + g) fetches it from that group's first lane
+            const uint32_t mine = __shfl_sync(0xffffffffu, word, ((lane - u * E) & (E - 1)) * LPW);
+            if (lane >= u * E && lane < (u + 1) * E) myword = mine;
+        }
+    } else {
+        for (int i0 = 0; i0 < MB_WORDS; i0 += MB_UNROLL) {
+            T v[MB_UNROLL];
+            if (full) {
+                const T *q = mb + (size_t)(w0 + i0) * 32 + lane;
+#pragma unroll
+                for (int u = 0; u < MB_UNROLL; ++u) v[u] = __ldg(q + u * 32);
+            } else {
+#pragma unroll
+                for (int u = 0; u < MB_UNROLL; ++u) {
+                    const int p = (w0 + i0 + u) * 32 + lane;
+                    v[u] = (T)0;
+                    if (p < HW) {
+                        long long off = p;
+                        if (!CONTIG) { const int y = p / W; off = (long long)y * sy + (long long)(p - y * W) * sx; }
+                        v[u] = __ldg(mb + off);
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < MB_UNROLL; ++u) {
-            uint32_t val;
-            bool sel;
-            if (MODE == PVB_SELECT_BYTE) { val = mask_byte<T>(v[u]); sel = val != 0; }
-            else { sel = (v[u] == (T)1); val = sel; }
-            const uint32_t word = __ballot_sync(0xffffffffu, sel);
-            if (lane == i0 + u) myword = word;
-            sum += val;
+            for (int u = 0; u < MB_UNROLL; ++u) {
+                uint32_t val;
+                bool sel;
+                mask_pred<T, MODE>(v[u], sel, val);
+                const uint32_t word = __ballot_sync(0xffffffffu, sel);
+                if (lane == i0 + u) myword = word;
+                sum += val;
+            }
         }
     }
     if (lane < MB_WORDS && w0 + lane < nwords) bits[(size_t)b * nwords + w0 + lane] = myword;
@@ -320,18 +355,26 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
 }
 
 // ---------------------------------------------------------------------------------
+// gather access pattern for an interleaved vertex tensor ([..,K,2] contiguous): 0 = auto = row-wise (consecutive lanes
+// read consecutive float2 of one pixel's 8*K-byte row: ~3 sectors per row and request instead of one sector per lane),
+// 1 = pixel-wise (one lane per pixel, K strided loads), 2 = row-wise.  Tooling / A-B measurements; results are identical.
+static std::atomic<int> g_gather_mode{0};
+void set_gather_tuning(int mode) { g_gather_mode.store(mode, std::memory_order_relaxed); }
+
 cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
 {
     const int nwords = a.nwords;
     dim3 g1((nwords + MB_WARPS * MB_WORDS - 1) / (MB_WARPS * MB_WORDS), a.B);
 #define PVB_MB2(T, MODE)                                                                                 \
     do {                                                                                                 \
+        const int vec_ok = contig && (reinterpret_cast<uintptr_t>(a.mask) % 16 == 0) &&                  \
+                           ((a.msb * (long long)sizeof(T)) % 16 == 0);                                   \
         if (contig)                                                                                      \
             mask_bits_kernel<T, MODE, true><<<g1, MB_WARPS * 32, 0, st>>>(                                \
-                (const T *)a.mask, a.msb, a.msy, a.msx, a.H, a.W, nwords, a.bits, a.fgsum, a.nz);        \
+                (const T *)a.mask, a.msb, a.msy, a.msx, a.H, a.W, nwords, a.bits, a.fgsum, a.nz, vec_ok); \
         else                                                                                             \
             mask_bits_kernel<T, MODE, false><<<g1, MB_WARPS * 32, 0, st>>>(                               \
-                (const T *)a.mask, a.msb, a.msy, a.msx, a.H, a.W, nwords, a.bits, a.fgsum, a.nz);        \
+                (const T *)a.mask, a.msb, a.msy, a.msx, a.H, a.W, nwords, a.bits, a.fgsum, a.nz, 0);     \
     } while (0)
 #define PVB_MB(T)                                                                                        \
     do {                                                                                                 \
@@ -371,7 +414,8 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
     dim3 g3(a.nblocks, a.B);
     gather_kernel<<<g3, GA_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
                                                 a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
-                                                a.nblocks, a.K, a.cap, a.W, a.rowwise_gather);
+                                                a.nblocks, a.K, a.cap, a.W,
+                                                (a.rowwise_gather || g_gather_mode.load(std::memory_order_relaxed) != 1) ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -37,6 +37,7 @@ _MASK_DTYPES = {
 }
 
 _workspaces = {}
+_VALIDATE_CAPACITY = True      # tests switch it off to reach the device-side overflow report (PVB_ERR_CAPACITY)
 
 
 def _workspace(device, nbytes):
@@ -179,11 +180,12 @@ def _run(op, mask, vertex, hn, inlier_thresh, min_num, max_num, mean=None, idxs=
             seed = _draw_seed() if (idxs is None or selection is None) else 0
         if capacity is None and selection is not None:
             capacity = H * W
-        if capacity is not None:
-            # a too-small capacity would silently truncate the pixel set (the kernels clamp tn): refuse it up front
+        if capacity is not None and _VALIDATE_CAPACITY:
+            # a too-small capacity would silently truncate the pixel set (the kernels clamp tn and only the sticky status
+            # word, read by debug=True / pvb_read_status, says so): refuse it up front
             need = H * W if selection is not None else min(H * W, int(max_num + 8 * math.sqrt(max(max_num, 0)) + 64))
             if int(capacity) < need:
-                raise ValueError(f"capacity={capacity} cannot hold the selection (needs >= {need}; H*W is always safe)")
+                raise RuntimeError(f"capacity={capacity} cannot hold the selection (needs >= {need}; H*W is always safe)")
         d = _make_desc(mask, vertex, hn, inlier_thresh, min_num, max_num, select_mode, seed, img_base, capacity)
         nbytes = lib.pvb_workspace_bytes(d)
         if nbytes == 0:

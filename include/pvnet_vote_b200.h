@@ -262,9 +262,11 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_FINISH = 3,   /* winner + refit, or covariance */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
-/* Tuning switch (tooling; process-wide, atomic).  reserved: pass 0.  vote_variant selects the pixel tile of the vote
- * kernel: 0 = 1 = 512 pixels (default), 2 = 256, 3 = 1024.  Results do not depend on it. */
-PVB_API int pvb_set_tuning(int32_t reserved, int32_t vote_variant);
+/* Tuning switches (tooling for A/B measurements; process-wide, atomic).  Results do not depend on them.
+ *   gather_mode  access pattern of the gather kernel on an interleaved vertex tensor: 0 = auto = 2 = row-wise (a warp reads
+ *                whole 8*K-byte pixel rows), 1 = pixel-wise (one lane per pixel)
+ *   vote_variant pixel tile of the vote kernel: 0 = 1 = 512 pixels (default), 2 = 256, 3 = 1024 */
+PVB_API int pvb_set_tuning(int32_t gather_mode, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);
 PVB_API int pvb_profile_read(double *ms, int32_t n);
 

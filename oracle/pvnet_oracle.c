@@ -62,7 +62,7 @@ ORC_API void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uin
 }
 
 /* Counter layout of the philox sampling mode (mirrored, independently, in
- * clean_pvnet_b200/csrc/philox.cuh).  tag: 1 = v3 pair indices, 2 = v3
+ * clean_pvnet_b200/csrc/common.cuh, philox4x32_10).  tag: 1 = v3 pair indices, 2 = v3
  * thinning, 3 = distribution pair indices, 4 = distribution thinning. */
 enum { ORC_TAG_V3_IDX = 1, ORC_TAG_V3_SEL = 2, ORC_TAG_DIST_IDX = 3, ORC_TAG_DIST_SEL = 4 };
 

@@ -125,13 +125,13 @@ def vote_variant():
     _lib.check(lib.pvb_set_tuning(0, 0))
 
 
-@pytest.mark.parametrize("variant", [1, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("tn,vn,hn,seed,thresh", [
     (1500, 2, 24, 20, 0.99), (2100, 3, 64, 21, 0.99), (3000, 2, 130, 22, 0.999), (1111, 2, 512, 23, 0.99),
     (2500, 1, 520, 24, 0.9), (1030, 2, 1100, 25, 0.99), (17, 1, 8, 26, 0.99), (1024, 1, 64, 27, 0.5)])
 def test_every_vote_kernel_matches_oracle(pvb, oracle, vote_variant, variant, tn, vn, hn, seed, thresh):
-    """Both vote kernels (FP32-pipe and tensor-path, every tile size) at hypothesis counts on both sides of the default
-    switch-over, with partial hypothesis groups, warp teams (hn < 512 on the tensor path) and partial pixel tiles."""
+    """Every launch shape of the vote kernel (pixel tile 512 / 256 / 1024; 1, 2 or 4 hypotheses per thread; 1, 2 or 4 warp
+    teams per CTA) at hypothesis counts on both sides of each switch-over, with partial slices and partial pixel tiles."""
     direct, coords, idxs, _ = field_case(tn, vn, hn, seed)
     hyp = oracle.generate_hypothesis(direct, coords, idxs)
     want = oracle.vote_count(direct, coords, hyp, thresh)
@@ -140,7 +140,7 @@ def test_every_vote_kernel_matches_oracle(pvb, oracle, vote_variant, variant, tn
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", [1, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_every_vote_kernel_adversarial(pvb, oracle, vote_variant, variant):
     """The adversarial case above under each kernel, plus hypotheses/pixels that force the exact path wholesale."""
     rng = np.random.default_rng(12)

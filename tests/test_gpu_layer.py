@@ -221,8 +221,16 @@ def test_error_paths(pvb):
     B, H, W = mask.shape
     sel = torch.zeros((B, H, W), device="cuda")           # keeps every foreground pixel
     big = torch.ones_like(mask)
-    with pytest.raises(RuntimeError, match="capacity"):
-        pvb.ransac_voting_layer_v3(big, vertex, 32, max_num=100, selection=sel, capacity=256, debug=True)
+    with pytest.raises(RuntimeError, match="cannot hold"):          # refused on the host, before anything is launched
+        pvb.ransac_voting_layer_v3(big, vertex, 32, max_num=100, selection=sel, capacity=256)
+    # ... and if a caller of the C ABI gets it wrong anyway, the device reports it (sticky status), nothing is overrun
+    from clean_pvnet_b200 import ransac_voting_gpu as op
+    op._VALIDATE_CAPACITY = False
+    try:
+        with pytest.raises(RuntimeError, match="selected more than capacity"):
+            pvb.ransac_voting_layer_v3(big, vertex, 32, max_num=100, selection=sel, capacity=256, debug=True)
+    finally:
+        op._VALIDATE_CAPACITY = True
 
 
 def test_empty_batch_and_empty_foreground(pvb):

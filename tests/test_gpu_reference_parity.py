@@ -94,27 +94,74 @@ def _exact_refit(ext, dbg, thresh):
     return out
 
 
-def test_v3_full_size_matches_reference(pvb, ref):
-    """cfg-2 shape, 2 images: thinning (fg ~ 92k > 30000) + 512 hypotheses, strided production layout.
+def _reference_refit_lines(ext, gpu, direct, coords, win, thresh):
+    """ransac_voting_gpu.py:177-196 as the reference executes them (fp32 torch ops: matmul, sum, its own b_inv) on a given
+    pixel ORDER -- the winner's inlier set does not depend on the order, the fp32 sums do."""
+    tn, vn = direct.shape[0], direct.shape[1]
+    normal = torch.zeros_like(direct)
+    normal[:, :, 0] = direct[:, :, 1]
+    normal[:, :, 1] = -direct[:, :, 0]
+    inl = torch.zeros([1, vn, tn], dtype=torch.uint8, device=direct.device)
+    ext.voting_for_hypothesis(direct, coords, win[None].contiguous(), inl, thresh)
+    inl = torch.squeeze(inl.float(), 0)
+    normal = normal.permute(1, 0, 2) * torch.unsqueeze(inl, 2)
+    b = torch.sum(normal * torch.unsqueeze(coords, 0), 2)
+    ATA = torch.matmul(normal.permute(0, 2, 1), normal)
+    ATb = torch.sum(normal * torch.unsqueeze(b, 2), 1)
+    return torch.matmul(gpu.b_inv(ATA), torch.unsqueeze(ATb, 2))[:, :, 0], inl.sum(1)
+
+
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_v3_full_size_matches_reference(pvb, ref, layout):
+    """The FULL cfg-2 batch (B=16, 480x640, K=9, hn=512, thinning: fg ~ 92k > 30000), both vertex layouts, same seed.
 
     With ~22 000 inliers per keypoint the reference's fp32 normal equations (cuBLAS matmul + torch.sum,
-    ransac_voting_gpu.py:189-193) carry ~1e-2 px of their own rounding noise on the ill-conditioned
-    out-of-image keypoint, so 1e-3 px agreement is not defined by the reference itself.  The test pins
-    what is: same winners, our refit within 1e-4 px of the exact (float64) value of the reference's
-    formula, and the whole reference-vs-ours gap explained by the reference's distance to that value."""
+    ransac_voting_gpu.py:189-193) carry their own rounding noise, largest on the ill-conditioned out-of-image keypoint;
+    `<1e-3 px vs reference` is therefore only defined up to the reference's distance to itself.  That distance is measured
+    here: the reference's own refit lines re-run on a PERMUTED pixel order (same inlier set, same formula, same fp32 ops).
+    Pinned: identical inlier sets; ours within 1e-4 px of the exact (float64) value of the reference's formula; the
+    ours-vs-reference gap explained by the reference's distance to that value; and ours-vs-reference no larger than a small
+    multiple of reference-vs-itself.  The numbers are written to gpurun_out/ for DESIGN.md / BASELINE.md."""
     ext, gpu = ref
-    mask, vertex, _ = _inputs("cfg2", seed=77, B=2, layout="planar")
+    mask, vertex, _ = _inputs("cfg2", seed=77, layout=layout)
     torch.manual_seed(3)
     want = gpu.ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99)
     torch.manual_seed(3)
     got, dbg = pvb.ransac_voting_layer_v3(mask, vertex, 512, inlier_thresh=0.99, rng="torch", debug=True)
     exact = _exact_refit(ext, dbg, 0.99)
-    ours_vs_exact = (got.double() - exact).norm(dim=-1).max().item()
+    ours_vs_exact = (got.double() - exact).norm(dim=-1)
     ref_vs_exact = (want.double() - exact).norm(dim=-1)
     ours_vs_ref = (got - want).norm(dim=-1)
-    assert ours_vs_exact < 1e-4, ours_vs_exact
+    # the reference against itself: identity order must reproduce its output, a permuted order shows its fp32 spread
+    B, K = got.shape[:2]
+    same_order = torch.zeros_like(want)
+    permuted = torch.zeros_like(want)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for b in range(B):
+        tn = int(dbg["tn"][b])
+        direct = dbg["dirs"][b, :, :tn].permute(1, 0, 2).contiguous()
+        coords = dbg["xy"][b, :tn].contiguous()
+        same_order[b], n0 = _reference_refit_lines(ext, gpu, direct, coords, dbg["win"][b], 0.99)
+        perm = torch.randperm(tn, generator=g, device="cuda")
+        permuted[b], n1 = _reference_refit_lines(ext, gpu, direct[perm].contiguous(), coords[perm].contiguous(), dbg["win"][b], 0.99)
+        assert torch.equal(n0, n1)                                   # the inlier SET is order independent
+    ref_vs_itself = (permuted - want).norm(dim=-1)
+    assert (same_order - want).norm(dim=-1).max().item() < 1e-4     # the helper is the reference's own computation
+    assert ours_vs_exact.max().item() < 1e-4, ours_vs_exact.max().item()
     assert (ours_vs_ref.double() <= ref_vs_exact + 2e-4).all(), (ours_vs_ref, ref_vs_exact)
-    assert ours_vs_ref.max().item() < 5e-2          # same consensus set; fp32 noise only (measured: 3e-4 .. 1.1e-2 px)
+    spread = max(ref_vs_itself.max().item(), ref_vs_exact.max().item())
+    assert ours_vs_ref.max().item() <= max(1e-3, 3.0 * spread), (ours_vs_ref.max().item(), spread)
+    inside = ours_vs_ref[:, :-1]                                     # keypoints inside the image (well conditioned)
+    report = dict(layout=layout, images=B, ours_vs_ref_max=ours_vs_ref.max().item(), ours_vs_ref_inside_max=inside.max().item(),
+                  ref_vs_itself_permuted_max=ref_vs_itself.max().item(), ref_vs_itself_inside_max=ref_vs_itself[:, :-1].max().item(),
+                  ref_vs_exact_max=ref_vs_exact.max().item(), ours_vs_exact_max=ours_vs_exact.max().item(),
+                  ours_below_1e3_fraction=float((ours_vs_ref < 1e-3).float().mean().item()))
+    import json
+    import os
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"r02_parity_cfg2_{layout}.json"), "w") as fh:
+            json.dump(report, fh, indent=1)
 
 
 def test_distribution_matches_reference_under_same_seed(pvb, ref):

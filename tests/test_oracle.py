@@ -183,3 +183,43 @@ def test_vanishing_point_pair(oracle):
     oracle.voting_for_hypothesis(direct, coords, hyp, inl, 0.999, vanishing_point=True)
     good = [h for h in range(32) if abs(hyp[h, 0, 2]) > 1e-3]
     assert inl[good].mean() > 0.9
+
+
+def test_cfg1_cpu_plumbing_case(oracle):
+    """BASELINE.json configs[0] ("single 128x128 synthetic mask + random unit-vector field, K=1, 64 hypotheses, CPU
+    reference path, plumbing, no GPU"): the oracle end to end on the CPU.  A pure random field has no consensus, so the
+    checks are structural: determinism, the winner is the first maximum of the counts, the counts equal the byte-tensor
+    formulation (voting_for_hypothesis + sum, ransac_voting_gpu.py:156-159), the refit is the least-squares point of the
+    winner's inliers, and the distribution op runs.  tests/test_gpu_configs.py::test_cfg1_plumbing_case compares the CUDA
+    path with exactly this."""
+    import time
+    import torch
+    from clean_pvnet_b200 import synth
+    mask, vertex, _ = synth.make_inputs("cfg1", device="cpu", seed=1235)
+    m, v = mask.numpy(), vertex.numpy()
+    assert m.shape == (1, 128, 128) and v.shape == (1, 128, 128, 1, 2)
+    t0 = time.perf_counter()
+    out, dbg = oracle.ransac_voting_layer_v3(m, v, 64, inlier_thresh=0.99, seed=11, debug=True)
+    dt = time.perf_counter() - t0
+    out2 = oracle.ransac_voting_layer_v3(m, v, 64, inlier_thresh=0.99, seed=11)
+    assert np.array_equal(out, out2) and np.isfinite(out).all()
+    tn = int(dbg["tn"][0])
+    assert tn == int(m.sum()) and 4000 < tn < 6000                    # ~30 % of 128*128, below max_num: no thinning
+    yx = np.argwhere(m[0] != 0)                                        # row-major = torch.nonzero order (:140)
+    coords = np.ascontiguousarray(yx[:, ::-1].astype(np.float32))      # (x, y)                      (:141)
+    direct = np.ascontiguousarray(v[0][m[0] != 0])                     # [tn,1,2] masked_select      (:142-143)
+    hyp = np.ascontiguousarray(dbg["hyp"][0].transpose(1, 0, 2))       # [hn,1,2]
+    inl = np.zeros((64, 1, tn), np.uint8)
+    oracle.voting_for_hypothesis(direct, coords, hyp, inl, 0.99)
+    counts = inl.sum(2).T                                              # [1,64]
+    assert np.array_equal(counts, dbg["counts"][0])
+    h = int(np.argmax(counts[0]))                                      # first maximum, like torch.max
+    assert np.array_equal(dbg["win"][0, 0], hyp[h, 0])
+    w = inl[h, 0].astype(np.float64)
+    n = np.stack([direct[:, 0, 1], -direct[:, 0, 0]], 1).astype(np.float64) * w[:, None]
+    b = (n * coords).sum(1)
+    x = np.linalg.solve(n.T @ n, n.T @ b)
+    assert np.abs(x - out[0, 0]).max() < 1e-3
+    _, cov = oracle.estimate_voting_distribution_with_mean(m, v, out, seed=12)
+    assert cov.shape == (1, 1, 2, 2) and np.isfinite(cov).all()
+    assert dt < 5.0                                                    # 64 x 5 000 tests: milliseconds on one core

@@ -19,11 +19,11 @@ ap.add_argument("--cfg", default="cfg2")
 ap.add_argument("--hn", type=int, default=512)
 ap.add_argument("--B", type=int, default=None)
 ap.add_argument("--dist", action="store_true", help="also run estimate_voting_distribution_with_mean")
-ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--gather", type=int, default=0, help="gather_mode of pvb_set_tuning")
 ap.add_argument("--variant", type=int, default=0)
 args = ap.parse_args()
 from clean_pvnet_b200 import _lib  # noqa: E402
-_lib.check(_lib.load().pvb_set_tuning(args.chunk, args.variant))
+_lib.check(_lib.load().pvb_set_tuning(args.gather, args.variant))
 mask, vertex, _ = synth.make_inputs(args.cfg, device="cuda", seed=1236, B=args.B)
 for i in range(args.steps):
     out = pvb.ransac_voting_layer_v3(mask, vertex, args.hn, inlier_thresh=0.99, seed=1000 + i)

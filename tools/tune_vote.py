@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cfg", default="cfg2")
 ap.add_argument("--hn", type=int, default=512)
 ap.add_argument("--steps", type=int, default=30)
-ap.add_argument("--chunks", default="0", help="reserved")
+ap.add_argument("--chunks", default="0", help="gather modes (pvb_set_tuning): 0 auto, 1 pixel-wise, 2 row-wise")
 ap.add_argument("--variants", default="0,1")
 args = ap.parse_args()
 lib = _lib.load()
@@ -38,5 +38,5 @@ for variant in [int(v) for v in args.variants.split(",")]:
         ms = (ctypes.c_double * 4)()
         n = lib.pvb_profile_read(ms, 4)
         lib.pvb_profile_enable(0)
-        print(f"variant={variant} step={e0.elapsed_time(e1)/args.steps:.4f} ms  "
+        print(f"variant={variant} gather={chunk} step={e0.elapsed_time(e1)/args.steps:.4f} ms  "
               f"select={ms[0]/n:.4f} gen={ms[1]/n:.4f} vote={ms[2]/n:.4f} refit={ms[3]/n:.4f}  same_result={same}")

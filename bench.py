@@ -548,7 +548,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD, choices=["cfg2", "cfg4"])
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "collective"],
                     help="N>1: how every rank's keypoints reach every rank (clean_pvnet_b200/parallel.py)")
-    ap.add_argument("--chunk", type=int, default=2, help="images per H2D chunk of the end-to-end path")
+    ap.add_argument("--chunk", type=int, default=4, help="images per H2D chunk of the end-to-end path")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true",

@@ -60,6 +60,8 @@ SIGNATURES = {
     "pvb_uncertainty_weights": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "pvb_uncertainty_pnp": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_void_p, _vp]),
+    "pvb_uncertainty_pnp_from_votes": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, _vp]),
     "pvb_uncertainty_pnp_init": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, ctypes.c_int64, ctypes.c_int64, _vp]),
     "pvb_read_status": (ctypes.c_int, [_dp, _vp, _vp]),
     "pvb_host_scratch_bytes": (_sz, [_dp, _i32]),

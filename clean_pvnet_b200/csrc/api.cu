@@ -202,7 +202,7 @@ int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
     if (e != cudaSuccess) return cuda_fail(e, "generate kernel");
     prof_end(pc, PVB_STAGE_GENERATE, st);
     prof_start(pc, PVB_STAGE_VOTE, st);
-    e = launch_vote(P.v, st);
+    e = launch_vote(P.v, false, st);
     if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
     prof_end(pc, PVB_STAGE_VOTE, st);
     return PVB_OK;
@@ -379,6 +379,35 @@ PVB_API int pvb_uncertainty_pnp(const double *pts2d, const double *pts3d, const 
     }
     cudaError_t e = launch_pnp(a, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "uncertainty pnp kernel");
+}
+
+PVB_API int pvb_uncertainty_pnp_from_votes(const float *kpt_2d, const float *cov, const float *weights, const double *pts3d,
+                                           const double *K, const double *init_rt, double *result_rt, double *init_out,
+                                           float *weights_out, int32_t *info, int32_t n, int32_t pn, int64_t pts3d_stride,
+                                           int64_t k_stride, const pvb_pnp_options *options, pvb_stream_t stream)
+{
+    if (n < 0) return fail(PVB_ERR_INVALID, "n < 0");
+    if (pn < 1 || pn > PNP_FUSED_MAX_PN) return fail(PVB_ERR_INVALID, "pn must be in [1,%d] (got %d)", PNP_FUSED_MAX_PN, pn);
+    if (!init_rt && pn < 4) return fail(PVB_ERR_INVALID, "the P3P initialisation needs pn >= 4 (got %d)", pn);
+    if (n && (!kpt_2d || !pts3d || !K || !result_rt)) return fail(PVB_ERR_INVALID, "NULL tensor");
+    if (n && ((cov == nullptr) == (weights == nullptr))) return fail(PVB_ERR_INVALID, "pass exactly one of cov / weights");
+    if (pts3d_stride < 0 || k_stride < 0) return fail(PVB_ERR_INVALID, "negative stride");
+    if ((reinterpret_cast<uintptr_t>(kpt_2d) & 7u) || (reinterpret_cast<uintptr_t>(cov) & 15u))
+        return fail(PVB_ERR_INVALID, "kpt_2d must be 8-byte and cov 16-byte aligned");
+    PnpFusedArgs a;
+    a.kpt2d = kpt_2d; a.cov = cov; a.weights = weights; a.pts3d = pts3d; a.K = K; a.init_rt = init_rt; a.result_rt = result_rt;
+    a.init_out = init_out; a.weights_out = weights_out; a.info = info; a.n = n; a.pn = pn;
+    a.pts3d_stride = pts3d_stride; a.k_stride = k_stride;
+    a.max_num_iterations = 50; a.function_tolerance = 1e-6; a.gradient_tolerance = 1e-10; a.parameter_tolerance = 1e-8;
+    if (options) {
+        if (options->max_num_iterations < 0 || !(options->function_tolerance >= 0.0) || !(options->gradient_tolerance >= 0.0) ||
+            !(options->parameter_tolerance >= 0.0))
+            return fail(PVB_ERR_INVALID, "pvb_pnp_options: negative or NaN entry");
+        a.max_num_iterations = options->max_num_iterations; a.function_tolerance = options->function_tolerance;
+        a.gradient_tolerance = options->gradient_tolerance; a.parameter_tolerance = options->parameter_tolerance;
+    }
+    cudaError_t e = launch_pnp_fused(a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? PVB_OK : cuda_fail(e, "fused uncertainty pnp kernel");
 }
 
 PVB_API int pvb_uncertainty_pnp_init(const double *pts2d, const double *pts3d, const double *wgt2d, const double *K,
@@ -581,7 +610,7 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
         PeerPush none;
         memset(&none, 0, sizeof(none));
         e = launch_generate(P.v, hp->cmp);
-        if (e == cudaSuccess) e = launch_vote(P.v, hp->cmp);
+        if (e == cudaSuccess) e = launch_vote(P.v, false, hp->cmp);
         if (e == cudaSuccess) e = launch_refit(P.v, P.win, P.refit, reinterpret_cast<float *>(sb + S.out), none, hp->cmp);
         if (e != cudaSuccess) return cuda_fail(e, "compute kernels");
         e = cudaMemcpyAsync(reinterpret_cast<char *>(out_kpt_host) + (size_t)b0 * obytes, sb + S.out, (size_t)c * obytes, cudaMemcpyDeviceToHost, hp->cmp);
@@ -723,7 +752,7 @@ PVB_API int pvb_vote_count(const float *direct, const float *coords, const float
     v.B = 1; v.K = vn; v.hn = hn; v.cap = tn; v.W = 0; v.H = 0; v.thresh = inlier_thresh;
     v.tn = meta; v.state = meta + 1; v.xy = xy;
     v.dirs = dirs; v.idxs = nullptr; v.hyp = hyp_k; v.counts = counts_k;
-    e = launch_vote(v, st);
+    e = launch_vote(v, true, st);
     if (e != cudaSuccess) return cuda_fail(e, "vote kernel");
     e = launch_compat_unpack_counts(counts_k, counts, vn, hn, st);
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "unpack");

@@ -87,6 +87,26 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
+// inv(sqrtm(cov)) of one 2x2 covariance, packed (wxx, wxy, wyy) and rounded to fp32 -- SURVEY 8f row 2
+// (lib/evaluators/linemod/pvnet.py:118-130: scipy.linalg.sqrtm + np.linalg.inv per keypoint on the CPU).
+// Closed form for a symmetric positive definite 2x2 M: sqrt(M) = (M + s I)/t, s = sqrt(det M), t = sqrt(tr M + 2 s),
+// so inv(sqrt(M)) = t * adj(M + s I) / det(M + s I).  cov[0,0] < 1e-6 or any NaN -> zeros, like the reference.
+__device__ __forceinline__ void cov_to_weights(const float4 c, float &o0, float &o1, float &o2)
+{
+    o0 = 0.f; o1 = 0.f; o2 = 0.f;
+    const bool bad = (c.x < 1e-6f) || (c.x != c.x) || (c.y != c.y) || (c.z != c.z) || (c.w != c.w);
+    if (!bad) {
+        const double a = c.x, b = 0.5 * ((double)c.y + (double)c.z), d = c.w;
+        const double det = a * d - b * b;
+        if (det > 0.0) {
+            const double s = sqrt(det), t = sqrt(a + d + 2.0 * s);
+            const double a2 = a + s, d2 = d + s;
+            const double den = a2 * d2 - b * b;
+            o0 = (float)(t * d2 / den); o1 = (float)(-t * b / den); o2 = (float)(t * a2 / den);
+        }
+    }
+}
+
 // Parameters of the cone test used by the fast path of the vote kernel (vote.cu).
 struct ConeParams {
     float kappa;   // tan(acos(thresh)) = sqrt(1-t^2)/t

@@ -42,10 +42,10 @@ struct VoteArgs {
     float2 *hyp;          // [B][K][hn]
     int *counts;          // [B][K][hn]
 };
-// hypotheses for every (image, keypoint): explicit idxs or philox
+// hypotheses for every (image, keypoint): explicit idxs or philox; also zeroes counts[b][k][h]
 cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st);
-// counts[b][k][h] = #pixels voting for hyp[b][k][h]   (zeroes counts itself)
-cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st);
+// counts[b][k][h] += #pixels voting for hyp[b][k][h]; launch_generate zeroes counts, other callers pass zero_counts = true
+cudaError_t launch_vote(const VoteArgs &a, bool zero_counts, cudaStream_t st);
 void set_vote_tuning(int variant);   // tooling: pixel-tile size per CTA
 void set_gather_tuning(int mode);    // tooling: gather access pattern (select.cu)
 // argmax + winner refit -> out_kpt [B][K][2], win [B][K].  The pixels of one (image,keypoint) are split
@@ -94,6 +94,26 @@ struct PnpArgs {
 cudaError_t launch_pnp(const PnpArgs &a, cudaStream_t st);
 // initial poses by P3P on the 4 best-weighted points (uses pts2d/pts3d/wgt2d/K, writes result_rt)
 cudaError_t launch_p3p_init(const PnpArgs &a, cudaStream_t st);
+
+// the un_pnp tail in one launch (pnp.cu): fp32 keypoints + covariances (or weights) in, refined poses out
+constexpr int PNP_FUSED_MAX_PN = 64;
+struct PnpFusedArgs {
+    const float *kpt2d;       // [n][pn][2]  (the voting layer's kpt_2d)
+    const float *cov;         // [n][pn][2][2] (the voting layer's var), or NULL ...
+    const float *weights;     // ... then [n][pn][3] precomputed (wxx, wxy, wyy)
+    const double *pts3d;      // [pn][3], problem p at pts3d + p*pts3d_stride (0: shared)
+    const double *K;          // [3][3] row-major, problem p at K + p*k_stride (0: shared)
+    const double *init_rt;    // optional [n][6]; NULL: P3P on the four best-weighted points
+    double *result_rt;        // [n][6]
+    double *init_out;         // optional [n][6]: the initial pose that was used
+    float *weights_out;       // optional [n][pn][3]
+    int *info;                // optional [n][2]
+    int n, pn;
+    long long pts3d_stride, k_stride;
+    int max_num_iterations;
+    double function_tolerance, gradient_tolerance, parameter_tolerance;
+};
+cudaError_t launch_pnp_fused(const PnpFusedArgs &a, cudaStream_t st);
 
 // twins of the reference extension on its own layouts
 cudaError_t launch_compat_generate(const float *direct, const float *coords, const int32_t *idxs, float *hyp,

@@ -355,9 +355,12 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
 }
 
 // ---------------------------------------------------------------------------------
-// gather access pattern for an interleaved vertex tensor ([..,K,2] contiguous): 0 = auto = row-wise (consecutive lanes
-// read consecutive float2 of one pixel's 8*K-byte row: ~3 sectors per row and request instead of one sector per lane),
-// 1 = pixel-wise (one lane per pixel, K strided loads), 2 = row-wise.  Tooling / A-B measurements; results are identical.
+// gather access pattern for an interleaved vertex tensor ([..,K,2] contiguous) in DEVICE memory: 0 = auto = 1 = pixel-wise
+// (one lane per pixel, K independent loads in flight per lane), 2 = row-wise (consecutive lanes read consecutive float2 of
+// one pixel's 8*K-byte row).  Measured on B200 at cfg-2 (profiles/r02_gather_modes.txt): select stage 60.6 us pixel-wise,
+// 71.1 us row-wise -- the kernel is latency-bound and the pixel-wise walk keeps 9 loads per lane in flight.  Pinned HOST
+// memory read in place is always fetched row-wise (a PCIe read is charged per 128-byte line touched, tools/pcie_probe.cu).
+// Tooling / A-B measurements; results are identical.
 static std::atomic<int> g_gather_mode{0};
 void set_gather_tuning(int mode) { g_gather_mode.store(mode, std::memory_order_relaxed); }
 
@@ -415,7 +418,7 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
     gather_kernel<<<g3, GA_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
                                                 a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
                                                 a.nblocks, a.K, a.cap, a.W,
-                                                (a.rowwise_gather || g_gather_mode.load(std::memory_order_relaxed) != 1) ? 1 : 0);
+                                                (a.rowwise_gather || g_gather_mode.load(std::memory_order_relaxed) == 2) ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -61,6 +61,7 @@ generate_kernel(VoteArgs a)
         }
     }
     a.hyp[((size_t)b * a.K + k) * a.hn + h] = make_float2(x, y);
+    a.counts[((size_t)b * a.K + k) * a.hn + h] = 0;      // the vote kernel accumulates with atomics: saves a memset launch
 }
 
 cudaError_t launch_generate(const VoteArgs &a, cudaStream_t st)
@@ -298,10 +299,12 @@ static std::atomic<int> g_vote_variant{0};
 
 void set_vote_tuning(int variant) { g_vote_variant.store(variant, std::memory_order_relaxed); }
 
-cudaError_t launch_vote(const VoteArgs &a, cudaStream_t st)
+cudaError_t launch_vote(const VoteArgs &a, bool zero_counts, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(a.counts, 0, sizeof(int) * (size_t)a.B * a.K * a.hn, st);
-    if (e != cudaSuccess) return e;
+    if (zero_counts) {     // callers that did not run generate_kernel (which zeroes the counts it creates hypotheses for)
+        cudaError_t e = cudaMemsetAsync(a.counts, 0, sizeof(int) * (size_t)a.B * a.K * a.hn, st);
+        if (e != cudaSuccess) return e;
+    }
     VoteK p;
     p.a = a;
     p.cone = make_cone(a.thresh);
@@ -530,28 +533,15 @@ cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_c
 
 // ---------------------------------------------------------------------------------
 // weights of the uncertainty PnP, inv(sqrtm(cov)) per keypoint packed as (wxx, wxy, wyy)
-// (lib/evaluators/linemod/pvnet.py:118-130: scipy.linalg.sqrtm + np.linalg.inv per keypoint on the CPU).
-// Closed form for a symmetric positive definite 2x2 M: sqrt(M) = (M + s I)/t, s = sqrt(det M), t = sqrt(tr M + 2 s),
-// so inv(sqrt(M)) = t * adj(M + s I) / det(M + s I).  cov[0,0] < 1e-6 or any NaN -> zeros, like the reference.
+// (cov_to_weights in common.cuh; the fused un_pnp tail in pnp.cu uses the same function).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 pnp_weights_kernel(const float *__restrict__ cov, float *__restrict__ w, int n)
 {
     const int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
-    const float4 c = __ldg(reinterpret_cast<const float4 *>(cov) + i);
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-    const bool bad = (c.x < 1e-6f) || (c.x != c.x) || (c.y != c.y) || (c.z != c.z) || (c.w != c.w);
-    if (!bad) {
-        const double a = c.x, b = 0.5 * ((double)c.y + (double)c.z), d = c.w;
-        const double det = a * d - b * b;
-        if (det > 0.0) {
-            const double s = sqrt(det), t = sqrt(a + d + 2.0 * s);
-            const double a2 = a + s, d2 = d + s;
-            const double den = a2 * d2 - b * b;
-            o0 = (float)(t * d2 / den); o1 = (float)(-t * b / den); o2 = (float)(t * a2 / den);
-        }
-    }
+    float o0, o1, o2;
+    cov_to_weights(__ldg(reinterpret_cast<const float4 *>(cov) + i), o0, o1, o2);
     w[(size_t)i * 3] = o0; w[(size_t)i * 3 + 1] = o1; w[(size_t)i * 3 + 2] = o2;
 }
 

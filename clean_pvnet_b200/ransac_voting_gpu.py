@@ -275,7 +275,7 @@ _host_scratch = {}
 
 
 def ransac_voting_layer_v3_host(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
-                                min_num=5, max_num=30000, *, device=None, chunk_images=2, seed=None, img_base=0,
+                                min_num=5, max_num=30000, *, device=None, chunk_images=4, seed=None, img_base=0,
                                 out=None, mode="auto"):
     """ransac_voting_layer_v3 for HOST tensors: the C ABI's host-buffer entry (pvb_ransac_voting_v3_host)
     processes the batch in `chunk_images`-sized pieces on three streams and writes keypoints to a host tensor.

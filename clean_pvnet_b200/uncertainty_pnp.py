@@ -5,12 +5,14 @@
     uncertainty_pnp_v2(points_2d, covars, points_3d, camera_matrix)         un_pnp_utils.py:60-121
     uncertainty_pnp_batch(...)                                              n problems in one launch, CUDA tensors in/out
     p3p_init_batch(...)                                                     the P3P initial poses for a batch, on the device
+    uncertainty_pnp_from_votes(kpt_2d, var, ...)                            weights + P3P + refinement in ONE launch, fp32 in
 
 The numpy twins keep the reference's initial pose: OpenCV P3P on the 4 best-weighted points (`cv2.solvePnP(..., SOLVEPNP_P3P)`,
 un_pnp_utils.py:27-31) on the host, or an `init_rt` you pass (the pose of a plain PnP, of the previous frame, ...).  The
 batched entry can also take it from `p3p_init_batch` -- the same recipe on the device (csrc/p3p_core.cuh, pinned against
-cv2.solvePnP on the CPU; experimental until its first GPU run).  The refinement runs on the GPU in fp64 with Ceres 2.0's
-default Levenberg-Marquardt options restated (include/pvnet_vote_b200.h); there is no CPU implementation behind it.
+cv2.solvePnP on the CPU and on the GPU box).  The refinement runs on the GPU in fp64 with Ceres 2.0's default
+Levenberg-Marquardt loop, pinned against the reference's own Ceres binary (tests/golden/ceres_pnp.npz); there is no CPU
+implementation behind it.
 """
 import ctypes
 
@@ -33,7 +35,7 @@ def uncertainty_pnp_batch(points_2d, weights_2d, points_3d, camera_matrix, init_
     """points_2d [n,pn,2], weights_2d [n,pn,3] (wxx,wxy,wyy), points_3d [pn,3] or [n,pn,3], camera_matrix [3,3] or [n,3,3],
     init_rt [n,6] (angle-axis, translation): CUDA tensors of any float dtype.  Returns result_rt [n,6] float64 on the same
     device (and info [n,2] int32 = iterations, termination code when return_info).  Stream-ordered, no host sync.
-    init_rt=None: the initial poses come from `p3p_init_batch` (the reference's P3P recipe, on the device; experimental)."""
+    init_rt=None: the initial poses come from `p3p_init_batch` (the reference's P3P recipe, on the device)."""
     if not (isinstance(points_2d, torch.Tensor) and points_2d.is_cuda):
         raise RuntimeError("points_2d must be a CUDA tensor")
     dev = points_2d.device
@@ -72,6 +74,71 @@ def uncertainty_pnp_batch(points_2d, weights_2d, points_3d, camera_matrix, init_
     return (out, info) if return_info else out
 
 
+def uncertainty_pnp_from_votes(kpt_2d, var, points_3d, camera_matrix, init_rt=None, *, weights=None, max_num_iterations=50,
+                               function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8,
+                               return_info=False, return_aux=False):
+    """The evaluator's whole un_pnp tail in ONE launch, straight from the voting layer's outputs (SURVEY 8f rows 2+3):
+
+        kpt_2d [n,pn,2] float32, var [n,pn,2,2] float32  = decode_keypoint's output['kpt_2d'], output['var']
+        -> weights = inv(sqrtm(var))            (lib/evaluators/linemod/pvnet.py:118-130, a scipy loop per keypoint)
+        -> P3P on the four best-weighted points  (un_pnp_utils.py:25-31, OpenCV on the CPU)       [unless init_rt is given]
+        -> Levenberg-Marquardt refinement        (un_pnp_utils.py:49-53 -> Ceres on the CPU)
+        -> result_rt [n,6] float64 (angle-axis, translation) on the same device; `rodrigues()` turns it into [n,3,4].
+
+    points_3d [pn,3] or [n,pn,3], camera_matrix [3,3] or [n,3,3] (any float dtype; converted to float64 once).  Pass
+    `weights` [n,pn,3] float32 instead of `var` (var=None) if they already exist.  Bit-identical to
+    uncertainty_pnp_weights -> p3p_init_batch -> uncertainty_pnp_batch.  No host sync.
+    return_info: also info [n,2] int32 (iterations, termination code); return_aux: also (init_rt used, weights)."""
+    if not (isinstance(kpt_2d, torch.Tensor) and kpt_2d.is_cuda):
+        raise RuntimeError("kpt_2d must be a CUDA tensor")
+    dev = kpt_2d.device
+    if kpt_2d.dim() != 3 or kpt_2d.shape[-1] != 2:
+        raise RuntimeError("kpt_2d must be [n,pn,2]")
+    n, pn = int(kpt_2d.shape[0]), int(kpt_2d.shape[1])
+    if (var is None) == (weights is None):
+        raise RuntimeError("pass exactly one of var / weights")
+    k2 = kpt_2d.float().contiguous()
+    cv = wt = None
+    if var is not None:
+        if tuple(var.shape) != (n, pn, 2, 2) or var.device != dev:
+            raise RuntimeError(f"var must be a CUDA tensor [{n},{pn},2,2] on {dev}")
+        cv = var.float().contiguous()
+    else:
+        if tuple(weights.shape) != (n, pn, 3) or weights.device != dev:
+            raise RuntimeError(f"weights must be a CUDA tensor [{n},{pn},3] on {dev}")
+        wt = weights.float().contiguous()
+    shared3, sharedk = points_3d.dim() == 2, camera_matrix.dim() == 2
+    if tuple(points_3d.shape[-2:]) != (pn, 3) or tuple(camera_matrix.shape[-2:]) != (3, 3):
+        raise RuntimeError("points_3d must be [pn,3] | [n,pn,3] and camera_matrix [3,3] | [n,3,3]")
+    p3 = points_3d.to(device=dev, dtype=torch.float64).contiguous()
+    km = camera_matrix.to(device=dev, dtype=torch.float64).contiguous()
+    rt0 = None
+    if init_rt is not None:
+        if tuple(init_rt.shape) != (n, 6):
+            raise RuntimeError("init_rt must be [n,6]")
+        rt0 = init_rt.to(device=dev, dtype=torch.float64).contiguous()
+    out = torch.empty((n, 6), dtype=torch.float64, device=dev)
+    info = torch.zeros((n, 2), dtype=torch.int32, device=dev) if return_info else None
+    init_out = torch.empty((n, 6), dtype=torch.float64, device=dev) if return_aux else None
+    w_out = torch.empty((n, pn, 3), dtype=torch.float32, device=dev) if return_aux else None
+    if n:
+        lib = _lib.load()
+        opt = _options(max_num_iterations, function_tolerance, gradient_tolerance, parameter_tolerance)
+        vp = ctypes.c_void_p
+        ptr = lambda t: vp(t.data_ptr()) if t is not None else None   # noqa: E731
+        with torch.cuda.device(dev):
+            _lib.check(lib.pvb_uncertainty_pnp_from_votes(
+                ptr(k2), ptr(cv), ptr(wt), ptr(p3), ptr(km), ptr(rt0), ptr(out), ptr(init_out), ptr(w_out), ptr(info), n, pn,
+                0 if shared3 else pn * 3, 0 if sharedk else 9, ctypes.cast(ctypes.pointer(opt), vp),
+                vp(torch.cuda.current_stream(dev).cuda_stream)))
+    res = (out,)
+    if return_info:
+        res += (info,)
+    if return_aux:
+        res += (init_out, w_out)
+    return res if len(res) > 1 else out
+
+
 def _p3p_init_prepared(p2, p3, w2, km, shared3, sharedk):
     n, pn = int(p2.shape[0]), int(p2.shape[1])
     if pn < 4:
@@ -90,7 +157,7 @@ def _p3p_init_prepared(p2, p3, w2, km, shared3, sharedk):
 def p3p_init_batch(points_2d, weights_2d, points_3d, camera_matrix):
     """Initial poses [n,6] as un_pnp_utils.py:25-31 computes them with OpenCV (P3P on the 2nd..4th best-weighted keypoints by
     wxx+wxy, the best one picks the root), on the device and for the whole batch; NaN rows where no pose is admissible.
-    EXPERIMENTAL in round 1: pinned against cv2.solvePnP on the CPU (tests/test_p3p_host_core.py), first GPU run pending."""
+    Pinned against cv2.solvePnP on the CPU (tests/test_p3p_host_core.py) and on the GPU (tests/test_gpu_zz_p3p.py)."""
     if not (isinstance(points_2d, torch.Tensor) and points_2d.is_cuda):
         raise RuntimeError("points_2d must be a CUDA tensor")
     dev = points_2d.device

@@ -19,7 +19,8 @@
  *   lib/networks/pvnet/resnet18.py:65-76  decode_keypoint         pvb_decode_v3 (+ pvb_estimate_voting_distribution)
  *   lib/evaluators/linemod/pvnet.py:118-130  weight loop          pvb_uncertainty_weights
  *   lib/csrc/uncertainty_pnp/src/ext.h  uncertainty_pnp(...)      pvb_uncertainty_pnp (batched)
- *   un_pnp_utils.py:25-31  cv2.solvePnP(..., SOLVEPNP_P3P)        pvb_uncertainty_pnp_init (experimental)
+ *   un_pnp_utils.py:25-31  cv2.solvePnP(..., SOLVEPNP_P3P)        pvb_uncertainty_pnp_init
+ *   evaluators/linemod/pvnet.py:118-130 + un_pnp_utils.py:6-57     pvb_uncertainty_pnp_from_votes (all three, one launch)
  *
  * Conventions
  *   - plain C: device pointers, sizes, strides (in ELEMENTS), a CUDA stream
@@ -174,8 +175,9 @@ PVB_API int pvb_uncertainty_weights(const float *cov, float *weights, int32_t n,
 /* Batched twin of the reference's C entry `uncertainty_pnp(pts2d, pts3d, wgt2d, K, init_rt, result_rt, pn)`
  * (lib/csrc/uncertainty_pnp/src/ext.h:1-9, uncertainty_pnp.cpp:61-92; bound through cffi by un_pnp_utils.py:49-53): refines
  * n poses (angle-axis + translation, 6 doubles) by minimising the weighted reprojection error of pn points each with the
- * Levenberg-Marquardt trust-region loop and the default options of Ceres Solver 2.0 (the reference's minimiser; DESIGN.md
- * section 8 says what of it is and is not pinned).  One warp per problem, fp64 like the reference.
+ * Levenberg-Marquardt trust-region loop and the default options of Ceres Solver 2.0 (the reference's minimiser; pinned
+ * against the reference's own Ceres binary: tests/golden/ceres_pnp.npz).  One warp per problem, fp64
+ * like the reference.
  * All pointers are DEVICE memory: pts2d [n,pn,2], wgt2d [n,pn,3] = (wxx,wxy,wyy), init_rt / result_rt [n,6],
  * pts3d [pn,3] and K [3,3] (row-major) per problem at pts3d + p*pts3d_stride / K + p*k_stride (strides in doubles; 0 = one
  * array shared by all problems), info optional int32 [n,2] = (iterations, termination: 1 gradient, 2 parameter, 3 function
@@ -191,12 +193,25 @@ PVB_API int pvb_uncertainty_pnp(const double *pts2d, const double *pts3d, const 
                                 const double *init_rt, double *result_rt, int32_t *info, int32_t n, int32_t pn,
                                 int64_t pts3d_stride, int64_t k_stride, const pvb_pnp_options *options, pvb_stream_t stream);
 
+/* The whole un_pnp tail of the evaluator in ONE launch, straight from the voting layer's fp32 outputs:
+ *   lib/evaluators/linemod/pvnet.py:118-130  weights = inv(sqrtm(var)) per keypoint          (pvb_uncertainty_weights)
+ *   un_pnp_utils.py:25-31                    P3P initial pose on the 4 best-weighted points  (pvb_uncertainty_pnp_init)
+ *   un_pnp_utils.py:49-53 -> ext.h           Ceres refinement                                (pvb_uncertainty_pnp)
+ * kpt_2d device fp32 [n,pn,2]; exactly one of cov (device fp32 [n,pn,2,2], 16-byte aligned) and weights (device fp32
+ * [n,pn,3]); pts3d / K as in pvb_uncertainty_pnp; init_rt optional [n,6] (NULL: P3P); result_rt [n,6]; optional outputs:
+ * init_out [n,6] (the initial pose used), weights_out fp32 [n,pn,3], info [n,2].  pn <= 64.  Bit-identical to running the
+ * three entry points one after the other on the same data (tests/test_gpu_pnp.py). */
+PVB_API int pvb_uncertainty_pnp_from_votes(const float *kpt_2d, const float *cov, const float *weights, const double *pts3d,
+                                           const double *K, const double *init_rt, double *result_rt, double *init_out,
+                                           float *weights_out, int32_t *info, int32_t n, int32_t pn, int64_t pts3d_stride,
+                                           int64_t k_stride, const pvb_pnp_options *options, pvb_stream_t stream);
+
 /* Initial poses for pvb_uncertainty_pnp, the reference's recipe on the device (un_pnp_utils.py:25-31:
  * `idxs = argsort(wxx + wxy)[-4:]`, `cv2.solvePnP(points_3d[idxs], points_2d[idxs], K, ..., flags=cv2.SOLVEPNP_P3P)`): P3P on
  * the 2nd..4th best-weighted keypoints, the best-weighted one chooses among the (up to four) poses by its reprojection
  * error.  Same layouts as pvb_uncertainty_pnp; writes init_rt [n,6] (angle-axis, translation); a problem without an
- * admissible solution gets NaNs (what OpenCV returns there).  pn >= 4.  EXPERIMENTAL in round 1: the arithmetic is pinned
- * against cv2.solvePnP on the CPU (tests/test_p3p_host_core.py), the device launch had no GPU time yet. */
+ * admissible solution gets NaNs (what OpenCV returns there).  pn >= 4.  The arithmetic is pinned against cv2.solvePnP on
+ * the CPU (tests/test_p3p_host_core.py), the device launch against OpenCV on the GPU box (tests/test_gpu_zz_p3p.py). */
 PVB_API int pvb_uncertainty_pnp_init(const double *pts2d, const double *pts3d, const double *wgt2d, const double *K,
                                      double *init_rt, int32_t n, int32_t pn, int64_t pts3d_stride, int64_t k_stride,
                                      pvb_stream_t stream);
@@ -263,8 +278,9 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
 /* Tuning switches (tooling for A/B measurements; process-wide, atomic).  Results do not depend on them.
- *   gather_mode  access pattern of the gather kernel on an interleaved vertex tensor: 0 = auto = 2 = row-wise (a warp reads
- *                whole 8*K-byte pixel rows), 1 = pixel-wise (one lane per pixel)
+ *   gather_mode  access pattern of the gather kernel on an interleaved vertex tensor in device memory: 0 = auto = 1 =
+ *                pixel-wise (one lane per pixel), 2 = row-wise (a warp reads whole 8*K-byte pixel rows; what in-place
+ *                host reads always use)
  *   vote_variant pixel tile of the vote kernel: 0 = 1 = 512 pixels (default), 2 = 256, 3 = 1024 */
 PVB_API int pvb_set_tuning(int32_t gather_mode, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);

@@ -176,3 +176,44 @@ def test_kernel_follows_real_ceres(pvb):
             else:
                 assert np.abs(rt[j] - G["result_rt"][i]).max() < 2e-4, i
     assert total >= 230 and same >= 0.97 * total, (same, total)
+
+
+def test_fused_tail_equals_the_three_step_pipeline(pvb):
+    """pvb_uncertainty_pnp_from_votes (weights + P3P + LM in one launch, fp32 in) against pvb_uncertainty_weights ->
+    pvb_uncertainty_pnp_init -> pvb_uncertainty_pnp on the same data: identical bits, incl. the degenerate covariances the
+    reference zeroes (cov[0,0] < 1e-6, NaN) and a problem whose P3P has no admissible pose."""
+    n, pn = 40, 9
+    cases = [pnp_case(1200 + s, pn=pn, noise=[0.5, 2.0][s % 2]) for s in range(n)]
+    rng = np.random.default_rng(5)
+    kpt = torch.from_numpy(np.stack([c[0] for c in cases])).float().cuda()
+    A = rng.normal(size=(n, pn, 2, 2))
+    cov = A @ A.transpose(0, 1, 3, 2) * rng.uniform(0.3, 5.0, size=(n, pn, 1, 1)) + 0.05 * np.eye(2)
+    cov[3, 2] = 0.0                       # cov[0,0] < 1e-6 -> weight 0
+    cov[4, 5, 0, 1] = np.nan              # NaN -> weight 0
+    cov[7, :, :, :] = 0.0                 # no usable keypoint at all: P3P has nothing, LM stops at once
+    cov = torch.from_numpy(cov).float().cuda()
+    model = torch.from_numpy(cases[0][1]).cuda()
+    cam = torch.from_numpy(cases[0][3]).cuda()
+    # re-project the shared model with every case's true pose so the problems are consistent
+    from clean_pvnet_b200.uncertainty_pnp import rodrigues
+    true = torch.from_numpy(np.stack([c[5] for c in cases])).cuda()
+    Rt = rodrigues(true)
+    camp = model[None] @ Rt[:, :, :3].transpose(1, 2) + Rt[:, None, :, 3]
+    uv = torch.stack([cam[0, 0] * camp[..., 0] / camp[..., 2] + cam[0, 2], cam[1, 1] * camp[..., 1] / camp[..., 2] + cam[1, 2]], -1)
+    kpt = (uv + torch.from_numpy(rng.normal(size=(n, pn, 2))).cuda()).float()
+    w = pvb.uncertainty_pnp_weights(cov)
+    init = pvb.p3p_init_batch(kpt, w, model, cam)
+    want, winfo = pvb.uncertainty_pnp_batch(kpt, w, model, cam, init, return_info=True)
+    got, info, init_used, w_used = pvb.uncertainty_pnp_from_votes(kpt, cov, model, cam, return_info=True, return_aux=True)
+    assert torch.equal(w_used, w)
+    assert torch.equal(init_used.view(torch.int64), init.view(torch.int64))          # NaN rows included
+    assert torch.equal(info, winfo)
+    assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    ok = torch.isfinite(got).all(dim=1)
+    assert int(ok.sum()) >= n - 3 and not bool(ok[7])
+    assert (got[ok][:, 3:] - true[ok][:, 3:]).abs().max().item() < 0.08              # and they are sensible poses
+    # the weights= form and an explicit init
+    got2 = pvb.uncertainty_pnp_from_votes(kpt, None, model, cam, init_rt=init, weights=w)
+    assert torch.equal(got2.view(torch.int64), want.view(torch.int64))
+    with pytest.raises(RuntimeError):
+        pvb.uncertainty_pnp_from_votes(kpt, cov, model, cam, weights=w)

@@ -345,6 +345,12 @@ def run_ours(args):
         init = torch.tensor([0.1, -0.2, 0.3, 0.0, 0.0, 0.9], device=dev, dtype=torch.float64).repeat(B, 1)
         extras["un_pnp_tail_ms"] = timed(
             lambda: pvb.uncertainty_pnp_batch(kp2d, pvb.uncertainty_pnp_weights(var), model, cam, init), 20)
+        # the same tail as ONE launch straight from the fp32 outputs (pvb_uncertainty_pnp_from_votes), same initial pose ...
+        extras["un_pnp_tail_fused_ms"] = timed(
+            lambda: pvb.uncertainty_pnp_from_votes(kp2d, var, model, cam, init), 20)
+        # ... and with the reference's P3P initialisation computed inside the launch (no init_rt)
+        extras["un_pnp_tail_fused_p3p_ms"] = timed(
+            lambda: pvb.uncertainty_pnp_from_votes(kp2d, var, model, cam), 20)
     except Exception as e:
         extras["un_pnp_error"] = str(e)
 

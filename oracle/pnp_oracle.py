@@ -8,19 +8,28 @@ Reference being restated
                                                             except linear_solver_type = DENSE_SCHUR, ceres::Solve.
     lib/csrc/uncertainty_pnp/un_pnp_utils.py:6-57           the Python caller (P3P initialisation with OpenCV, then the C entry)
 
-The minimiser is a third-party dependency that is NOT in /root/reference as source: Ceres Solver 2.0.0 (vendored as headers
-under lib/csrc/uncertainty_pnp/include/ceres + the prebuilt lib/libceres.so.2.0.0, which does not load in this container:
-libspqr / libcholmod / liblapack / libglog are missing).  PARITY UNPINNED against Ceres itself.  What is restated here is its
-published algorithm with the default options (docs "Non-linear Least Squares", TRUST_REGION / LEVENBERG_MARQUARDT; option
-defaults in include/ceres/solver.h of the vendored headers):
+The minimiser is a third-party dependency that is NOT in /root/reference as source: Ceres Solver 2.0.0, vendored as headers
+under lib/csrc/uncertainty_pnp/include/ceres plus the prebuilt lib/libceres.so.2.0.0.  PARITY PINNED AGAINST THAT BINARY:
+oracle/build_ceres_ref.py loads it here (its six missing back-end libraries -- SuiteSparse, CXSparse, LAPACK/BLAS, gflags,
+libunwind -- are closed with abort-stubs; Ceres never calls them with DENSE_SCHUR + Eigen) and builds the reference's
+unmodified src/uncertainty_pnp.cpp against it; tests/golden/make_golden_ceres.py recorded 284 problems it solved
+(tests/golden/ceres_pnp.npz) and tests/test_ceres_golden.py holds this restatement to it: same stop reason, same number of
+iterations, same cost after every iteration, same pose to 1e-9 on every problem an independent implementation can follow
+(236 of them, incl. descents with up to 20 rejected steps and the 50-iteration cap; the rest are ill-conditioned 4-6 point
+problems whose trajectories amplify a last-bit difference ~10x per iteration, measured by re-running Ceres itself from
+init*(1+1e-13)).
+What is restated is Ceres' TRUST_REGION / LEVENBERG_MARQUARDT loop with the default options (include/ceres/solver.h of the
+vendored headers):
     max_num_iterations 50, function_tolerance 1e-6, gradient_tolerance 1e-10, parameter_tolerance 1e-8,
     initial_trust_region_radius 1e4, max 1e16, min 1e-32, min_relative_decrease 1e-3, min_lm_diagonal 1e-6,
     max_lm_diagonal 1e32, jacobi_scaling on, monotonic steps, max_num_consecutive_invalid_steps 5.
 The constants of the loop can be read in source form in the vendored header-only `include/ceres/tiny_solver.h:171-290`, the same
 authors' compact LM (Jacobi scaling 1/(1+|col|), LM diagonal sqrt(clamp(JtJ_ii, 1e-6, 1e32)/radius), radius /= max(1/3, 1-(2rho-1)^3)
-on acceptance, radius /= v, v *= 2 on rejection); the full minimiser adds min_relative_decrease, the function-tolerance test,
-invalid-step handling and evaluates the gradient test on the unscaled gradient -- restated here from its documentation.
-What IS pinned: the objective (against ceres/rotation.h:563-607 semantics and an independent finite-difference check) and the
+on acceptance, radius /= v, v *= 2 on rejection); the full minimiser adds min_relative_decrease, the function-tolerance test
+(which leaves the last candidate UNAPPLIED -- confirmed against the binary), invalid-step handling and evaluates the gradient
+test on the unscaled gradient.  With one 6-parameter block DENSE_SCHUR eliminates it as the only e-block, i.e. solves the
+6x6 regularised normal equations by Cholesky -- what `uncertainty_pnp` below does.
+Also pinned independently: the objective (against ceres/rotation.h:563-607 semantics and a finite-difference check) and the
 optimum (tests/test_pnp_oracle.py compares with scipy.optimize.least_squares on the same residuals).
 """
 import numpy as np

@@ -83,5 +83,36 @@ int main()
         const double payload = (double)nchunks * c.lanes * 8;
         printf("in-place %-62s payload %.1f MB: %.3f ms  %.1f GB/s payload\n", c.what, payload / 1e6, ms, payload / ms / 1e6);
     }
+    // ---- the same access patterns on DEVICE memory: what does HBM deliver for sparse rows?  (the gather kernel's roof)
+    printf("\n-- device memory (HBM3e), L2 flushed before every repetition --\n");
+    unsigned char *flush = nullptr;
+    CK(cudaMalloc((void **)&flush, (size_t)512 << 20));
+    for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaEventRecord(e0));
+        stream_read<<<148 * 16, 256>>>((const uint4 *)dev, bytes / 16, sink);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    printf("HBM contiguous 16-byte loads %zu MB: %.3f ms  %.1f GB/s\n", bytes >> 20, ms, bytes / ms / 1e6);
+    const Case dcases[] = {
+        {4, 0, "32 B chunks, stride 768"}, {8, 0, "64 B chunks, stride 768"}, {9, 0, "72 B rows, stride 720"},
+        {9, 8, "72 B rows, 8-B aligned starts, stride 720 (the gather's pattern)"}, {16, 0, "128 B chunks, stride 768"},
+        {32, 0, "256 B chunks, stride 2304"},
+    };
+    for (const Case &c : dcases) {
+        const size_t stride8 = (c.lanes == 9 ? 720 : (c.lanes <= 16 ? 768 : 2304)) / 8;
+        const size_t nchunks = (size_t)48 * 1024 * 1024 / (c.lanes * 8);
+        if ((nchunks * stride8 + 64) * 8 > bytes) { printf("skip %s\n", c.what); continue; }
+        for (int rep = 0; rep < 3; ++rep) {
+            CK(cudaMemsetAsync(flush, rep, (size_t)512 << 20));       // evict the 126 MB L2 between repetitions
+            CK(cudaEventRecord(e0));
+            chunk_read<<<148 * 16, 256>>>(dev, nchunks, c.lanes, stride8, c.skew_mod, sink);
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        const double payload = (double)nchunks * c.lanes * 8;
+        printf("HBM %-66s payload %.1f MB: %.4f ms  %.0f GB/s payload  (%.2f ns/chunk)\n", c.what, payload / 1e6, ms, payload / ms / 1e6,
+               ms * 1e6 / nchunks);
+    }
     return 0;
 }

@@ -15,6 +15,7 @@
 // All three kernels are HBM/latency bound: the mask is read exactly once (mask_bits), the
 // bitmap (1/256 of an int64 mask) is what later passes touch, and the vertex field is read
 // only at selected pixels.
+#include <algorithm>
 #include <atomic>
 #include "common.cuh"
 #include "kernels.h"
@@ -30,13 +31,24 @@ __device__ __forceinline__ uint32_t mask_byte<double>(double v) { return (uint32
 
 constexpr int MB_WARPS = 8;
 constexpr int MB_UNROLL = 8;
-constexpr int MB_WORDS = 16;     // bitmap words (of 32 pixels) per warp
+constexpr int MB_WORDS = 32;     // bitmap words (of 32 pixels) per warp: 1024 pixels, lane i keeps word i
 
-// One warp converts 512 pixels into 16 bitmap words; lane i keeps word i so the words leave as one coalesced store.
-//   VEC path (contiguous image, 16-byte aligned, all 512 pixels in range): every lane loads 16 BYTES per instruction
-//   (E = 16/sizeof(T) consecutive pixels: 2 for the int64 mask torch.argmax produces), all loads of the warp's span are
-//   issued before the first use -- 4 KB in flight per warp for int64 -- and the E-bit pieces of the 32/E lanes that
-//   share a bitmap word are OR-reduced with one REDUX per load instruction.
+// 16-byte streaming load (ld.global.cs: the mask is read exactly once -- evict-first in L2, so it does not push the
+// compacted dirs/xy arrays, which the vote kernel re-reads from L2, out to DRAM).  volatile: the compiler must not
+// narrow it to the 32-bit pieces the predicate happens to need (it did: 2x the LSU instructions, profiles/r02).
+__device__ __forceinline__ uint4 ld_stream16(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// One warp converts 1024 pixels into 32 bitmap words; lane i keeps word i so the words leave as one coalesced store.
+//   VEC path (contiguous image, 16-byte aligned, all 1024 pixels in range): every lane loads 16 BYTES per instruction
+//   (E = 16/sizeof(T) consecutive pixels: 2 for the int64 mask torch.argmax produces), 8 loads in flight per lane
+//   (4 KB per warp), two rounds for int64; the E-bit pieces of the 32/E lanes that share a bitmap word are OR-reduced
+//   with one REDUX per load instruction.  The grid is 38 x B CTAs of 8 warps: half a wave at cfg-2, so every CTA is
+//   resident from the start (the 512-pixel version needed 1.01 waves: a 16-CTA tail cost a quarter of the kernel).
 //   Scalar path (strided masks, image tail): one pixel per lane and load, MB_UNROLL loads in flight, ballots.
 template <typename T, int MODE>
 __device__ __forceinline__ void mask_pred(T v, bool &sel, uint32_t &val)
@@ -62,28 +74,33 @@ mask_bits_kernel(const T *__restrict__ mask, long long sb, long long sy, long lo
     if (full && vec_ok) {
         constexpr int E = 16 / (int)sizeof(T);            // pixels per lane and load
         constexpr int NL = MB_WORDS / E;                  // load instructions per warp (E words each)
+        constexpr int NR = NL < 8 ? NL : 8;               // loads in flight per lane and round (8 x 16 B = 4 KB per warp)
         constexpr int LPW = 32 / E;                       // lanes that share one bitmap word
         union V { uint4 u; T t[E]; };
-        V v[NL];
         const uint4 *q = reinterpret_cast<const uint4 *>(mb + (size_t)w0 * 32) + lane;
-#pragma unroll
-        for (int u = 0; u < NL; ++u) v[u].u = __ldg(q + u * 32);
-        const int grp = lane / LPW;                       // word (within the load) this lane contributes to
+        const int grp = lane / LPW;                       // word (within one load) this lane contributes to
         const uint32_t gmask = (LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u)) << (grp * LPW);
 #pragma unroll
-        for (int u = 0; u < NL; ++u) {
-            uint32_t lb = 0;
+        for (int r0 = 0; r0 < NL; r0 += NR) {
+            V v[NR];
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-                bool sel; uint32_t val;
-                mask_pred<T, MODE>(v[u].t[j], sel, val);
-                lb |= (sel ? 1u : 0u) << j;
-                sum += val;
+            for (int u = 0; u < NR; ++u) v[u].u = ld_stream16(q + (r0 + u) * 32);
+#pragma unroll
+            for (int u = 0; u < NR; ++u) {
+                const int g = r0 + u;                     // this load covers words [g*E, (g+1)*E)
+                uint32_t lb = 0;
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    bool sel; uint32_t val;
+                    mask_pred<T, MODE>(v[u].t[j], sel, val);
+                    lb |= (sel ? 1u : 0u) << j;
+                    sum += val;
+                }
+                const uint32_t word = __reduce_or_sync(gmask, lb << ((lane % LPW) * E));
+                // word (g*E + k) was assembled by lane group k; lane (g*E + k) fetches it from that group's first lane
+                const uint32_t mine = __shfl_sync(0xffffffffu, word, ((lane - g * E) & (E - 1)) * LPW);
+                if (lane >= g * E && lane < (g + 1) * E) myword = mine;
             }
-            const uint32_t word = __reduce_or_sync(gmask, lb << ((lane % LPW) * E));
-            // word (u*E + g) was assembled by group g; lane (u*E + g) fetches it from that group's first lane
-            const uint32_t mine = __shfl_sync(0xffffffffu, word, ((lane - u * E) & (E - 1)) * LPW);
-            if (lane >= u * E && lane < (u + 1) * E) myword = mine;
         }
     } else {
         for (int i0 = 0; i0 < MB_WORDS; i0 += MB_UNROLL) {
@@ -264,6 +281,7 @@ thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__
 // walks that dense list: every lane is active, loads touch only selected pixels, and each store
 // instruction of a warp writes 32 consecutive t of one keypoint plane of dirs[] (256 B).
 constexpr int GA_THREADS = TS_THREADS;
+constexpr int GA_SPAN_MAX_K = 40;      // span walk: 4 warps x 32 pixels x K x 8 bytes of shared memory (K = 40: 40 KB)
 
 __global__ void __launch_bounds__(GA_THREADS)
 gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff,
@@ -271,9 +289,11 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
               int *__restrict__ status, const float *__restrict__ vertex,
               long long sB, long long sH, long long sW, long long sK, long long sC,
               float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W,
-              int rowwise)
+              int rowwise, const int *__restrict__ nz, int HW, int span_mode)
 {
-    __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (12 bits)
+    // s_list (pixel-wise / row-wise walks) and the per-warp span buffers (span walk) share the dynamic shared memory
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    unsigned short *s_list = reinterpret_cast<unsigned short *>(s_dyn);   // [TS_THREADS*32] pixel index inside the block
     __shared__ int s_base;
     const int b = blockIdx.y, blk = blockIdx.x;
     if (state[b] != 0) return;
@@ -293,6 +313,52 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
         if (lane == 0) s_base = base;
     }
     const int w = blk * TS_THREADS + tid;
+    const float *vimg = vertex + (long long)b * sB;
+    // ---- span walk: the image is one contiguous [H*W][K][2] array and the selection is dense inside the foreground
+    // (no thinning, or thinning that keeps >= 1/5): sparse 72-byte rows reach only ~1.1 TB/s of payload on HBM3e
+    // (tools/pcie_probe.cu), a third of what contiguous reads deliver, so it is FASTER to stream the whole 32-pixel span
+    // of every bitmap word that has a selected pixel (K*256 contiguous bytes, 16-byte loads) through shared memory and
+    // pick the selected rows there.
+    const bool span_layout = (sC == 1 && sK == 2 && sW == 2LL * K && sH == (long long)W * sW && (sB & 3) == 0 &&
+                              (reinterpret_cast<uintptr_t>(vertex) & 15u) == 0 && K <= GA_SPAN_MAX_K);
+    const bool span = !rowwise && span_layout && (span_mode == 3 || (span_mode == 0 && (long long)tn[b] * 5 >= (long long)nz[b]));
+    if (span) {
+        uint32_t word = 0;
+        int o = 0;
+        if (w < nwords) { word = bits[(size_t)b * nwords + w]; o = wordoff[(size_t)b * nwords + w]; }
+        __syncthreads();                                   // s_base
+        const int base = s_base;
+        float2 *buf = reinterpret_cast<float2 *>(s_dyn) + (size_t)warp * 32 * K;       // this warp's span: [32][K] float2
+        const int nq = 16 * K;                             // 16-byte pieces of one span
+        const unsigned active = __ballot_sync(0xffffffffu, word != 0);
+        for (unsigned m = active; m; m &= m - 1) {
+            const int i = __ffs(m) - 1;                    // lane i holds this word
+            const uint32_t wd = __shfl_sync(0xffffffffu, word, i);
+            const int t0 = base + __shfl_sync(0xffffffffu, o, i);
+            const int p0 = (blk * TS_THREADS + warp * 32 + i) * 32;
+            const float4 *src = reinterpret_cast<const float4 *>(vimg + (long long)p0 * sW);
+            if (p0 + 32 <= HW) {
+                for (int q = lane; q < nq; q += 32) reinterpret_cast<float4 *>(buf)[q] = __ldcs(src + q);   // read once: evict-first
+            } else {                                       // the image's last, partial word: never read past the image
+                const float2 *src2 = reinterpret_cast<const float2 *>(src);
+                for (int q = lane; q < (HW - p0) * K; q += 32) buf[q] = __ldcs(src2 + q);
+            }
+            __syncwarp();
+            const int nsel = __popc(wd);
+            for (int e = lane; e < nsel * K; e += 32) {
+                const int k = e / nsel, r = e - k * nsel;
+                const int t = t0 + r;
+                if (t < cap) dirs[((size_t)b * K + k) * cap + t] = buf[(__fns(wd, 0, r + 1)) * K + k];
+            }
+            if (lane < nsel && t0 + lane < cap) {
+                const int p = p0 + (int)__fns(wd, 0, lane + 1);
+                const int y = p / W;
+                xy[(size_t)b * cap + t0 + lane] = make_float2((float)(p - y * W), (float)y);
+            }
+            __syncwarp();
+        }
+        return;
+    }
     if (w < nwords) {
         uint32_t word = bits[(size_t)b * nwords + w];
         int o = wordoff[(size_t)b * nwords + w];
@@ -306,7 +372,6 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
     const int base = s_base;
     const bool vec = (sC == 1 && (sK & 1) == 0 && (sW & 1) == 0 && (sH & 1) == 0 && (sB & 1) == 0 &&
                       (reinterpret_cast<uintptr_t>(vertex) & 7u) == 0);
-    const float *vimg = vertex + (long long)b * sB;
     if (rowwise && vec && sK == 2) {
         // vertex lives in pinned HOST memory (zero-copy entry): consecutive lanes read consecutive float2 of
         // the same pixel row so each selected pixel costs one contiguous 8*K-byte PCIe read, not K scattered ones
@@ -355,9 +420,10 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
 }
 
 // ---------------------------------------------------------------------------------
-// gather access pattern for an interleaved vertex tensor ([..,K,2] contiguous) in DEVICE memory: 0 = auto = 1 = pixel-wise
-// (one lane per pixel, K independent loads in flight per lane), 2 = row-wise (consecutive lanes read consecutive float2 of
-// one pixel's 8*K-byte row).  Measured on B200 at cfg-2 (profiles/r02_gather_modes.txt): select stage 60.6 us pixel-wise,
+// gather access pattern for an interleaved vertex tensor ([..,K,2] contiguous) in DEVICE memory: 0 = auto (span walk when
+// the image is contiguous and the selection keeps >= 1/5 of the foreground, else pixel-wise), 1 = pixel-wise (one lane per
+// pixel, K independent loads in flight per lane), 2 = row-wise (consecutive lanes read consecutive float2 of one pixel's
+// 8*K-byte row), 3 = span walk wherever the layout allows it.  Measured on B200 at cfg-2 (profiles/r02_gather_modes.txt): select stage 60.6 us pixel-wise,
 // 71.1 us row-wise -- the kernel is latency-bound and the pixel-wise walk keeps 9 loads per lane in flight.  Pinned HOST
 // memory read in place is always fetched row-wise (a PCIe read is charged per 128-byte line touched, tools/pcie_probe.cu).
 // Tooling / A-B measurements; results are identical.
@@ -415,10 +481,14 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 g3(a.nblocks, a.B);
-    gather_kernel<<<g3, GA_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
+    const int gmode = g_gather_mode.load(std::memory_order_relaxed);
+    size_t smem = sizeof(unsigned short) * TS_THREADS * 32;                       // s_list
+    if (a.K <= GA_SPAN_MAX_K) smem = std::max(smem, (size_t)(GA_THREADS / 32) * 32 * a.K * sizeof(float2));
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;                             // cannot happen for K <= GA_SPAN_MAX_K
+    gather_kernel<<<g3, GA_THREADS, smem, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
                                                 a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
-                                                a.nblocks, a.K, a.cap, a.W,
-                                                (a.rowwise_gather || g_gather_mode.load(std::memory_order_relaxed) == 2) ? 1 : 0);
+                                                a.nblocks, a.K, a.cap, a.W, (a.rowwise_gather || gmode == 2) ? 1 : 0,
+                                                a.nz, a.H * a.W, gmode);
     return cudaGetLastError();
 }
 

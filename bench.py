@@ -262,8 +262,10 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     last = None
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         last = step(i)
+    t_host1 = time.perf_counter()            # host time to ENQUEUE the steps (the GPU runs behind unless the host is the bottleneck)
     gathered = drain()
     ev1.record()
     torch.cuda.synchronize()
@@ -441,6 +443,8 @@ def run_ours(args):
                     "note": ("454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
                              "24 LDS); tools/microbench.cu bounds this mix at 610 cycles/block/SMSP => ~4.2 T tests/s")},
             "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
+            "host": {"enqueue_ms_per_step": (t_host1 - t_host0) * 1e3 / args.steps, "usable_cores": _usable_cores(),
+                     "note": "host time spent enqueueing one step (rank 0); if it approaches ms_per_step the GPU is launch-starved"},
             "extras": extras,
         }
         if gather_check is not None:

@@ -629,7 +629,7 @@ PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK;
 PVB_API int pvb_set_tuning(int32_t gather_mode, int32_t vote_variant)
 {
     if (vote_variant < 0 || vote_variant > 3) return fail(PVB_ERR_INVALID, "vote_variant must be 0..3");
-    if (gather_mode < 0 || gather_mode > 3) return fail(PVB_ERR_INVALID, "gather_mode must be 0..3");
+    if (gather_mode < 0 || gather_mode > 2) return fail(PVB_ERR_INVALID, "gather_mode must be 0..2");
     set_gather_tuning(gather_mode);
     set_vote_tuning(vote_variant);
     return PVB_OK;

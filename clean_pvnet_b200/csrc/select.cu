@@ -15,7 +15,6 @@
 // All three kernels are HBM/latency bound: the mask is read exactly once (mask_bits), the
 // bitmap (1/256 of an int64 mask) is what later passes touch, and the vertex field is read
 // only at selected pixels.
-#include <algorithm>
 #include <atomic>
 #include "common.cuh"
 #include "kernels.h"
@@ -281,7 +280,6 @@ thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__
 // walks that dense list: every lane is active, loads touch only selected pixels, and each store
 // instruction of a warp writes 32 consecutive t of one keypoint plane of dirs[] (256 B).
 constexpr int GA_THREADS = TS_THREADS;
-constexpr int GA_SPAN_MAX_K = 40;      // span walk: 4 warps x 32 pixels x K x 8 bytes of shared memory (K = 40: 40 KB)
 
 __global__ void __launch_bounds__(GA_THREADS)
 gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff,
@@ -289,11 +287,9 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
               int *__restrict__ status, const float *__restrict__ vertex,
               long long sB, long long sH, long long sW, long long sK, long long sC,
               float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W,
-              int rowwise, const int *__restrict__ nz, int HW, int span_mode)
+              int rowwise)
 {
-    // s_list (pixel-wise / row-wise walks) and the per-warp span buffers (span walk) share the dynamic shared memory
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    unsigned short *s_list = reinterpret_cast<unsigned short *>(s_dyn);   // [TS_THREADS*32] pixel index inside the block
+    __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (12 bits)
     __shared__ int s_base;
     const int b = blockIdx.y, blk = blockIdx.x;
     if (state[b] != 0) return;
@@ -314,51 +310,6 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
     }
     const int w = blk * TS_THREADS + tid;
     const float *vimg = vertex + (long long)b * sB;
-    // ---- span walk: the image is one contiguous [H*W][K][2] array and the selection is dense inside the foreground
-    // (no thinning, or thinning that keeps >= 1/5): sparse 72-byte rows reach only ~1.1 TB/s of payload on HBM3e
-    // (tools/pcie_probe.cu), a third of what contiguous reads deliver, so it is FASTER to stream the whole 32-pixel span
-    // of every bitmap word that has a selected pixel (K*256 contiguous bytes, 16-byte loads) through shared memory and
-    // pick the selected rows there.
-    const bool span_layout = (sC == 1 && sK == 2 && sW == 2LL * K && sH == (long long)W * sW && (sB & 3) == 0 &&
-                              (reinterpret_cast<uintptr_t>(vertex) & 15u) == 0 && K <= GA_SPAN_MAX_K);
-    const bool span = !rowwise && span_layout && (span_mode == 3 || (span_mode == 0 && (long long)tn[b] * 5 >= (long long)nz[b]));
-    if (span) {
-        uint32_t word = 0;
-        int o = 0;
-        if (w < nwords) { word = bits[(size_t)b * nwords + w]; o = wordoff[(size_t)b * nwords + w]; }
-        __syncthreads();                                   // s_base
-        const int base = s_base;
-        float2 *buf = reinterpret_cast<float2 *>(s_dyn) + (size_t)warp * 32 * K;       // this warp's span: [32][K] float2
-        const int nq = 16 * K;                             // 16-byte pieces of one span
-        const unsigned active = __ballot_sync(0xffffffffu, word != 0);
-        for (unsigned m = active; m; m &= m - 1) {
-            const int i = __ffs(m) - 1;                    // lane i holds this word
-            const uint32_t wd = __shfl_sync(0xffffffffu, word, i);
-            const int t0 = base + __shfl_sync(0xffffffffu, o, i);
-            const int p0 = (blk * TS_THREADS + warp * 32 + i) * 32;
-            const float4 *src = reinterpret_cast<const float4 *>(vimg + (long long)p0 * sW);
-            if (p0 + 32 <= HW) {
-                for (int q = lane; q < nq; q += 32) reinterpret_cast<float4 *>(buf)[q] = __ldcs(src + q);   // read once: evict-first
-            } else {                                       // the image's last, partial word: never read past the image
-                const float2 *src2 = reinterpret_cast<const float2 *>(src);
-                for (int q = lane; q < (HW - p0) * K; q += 32) buf[q] = __ldcs(src2 + q);
-            }
-            __syncwarp();
-            const int nsel = __popc(wd);
-            for (int e = lane; e < nsel * K; e += 32) {
-                const int k = e / nsel, r = e - k * nsel;
-                const int t = t0 + r;
-                if (t < cap) dirs[((size_t)b * K + k) * cap + t] = buf[(__fns(wd, 0, r + 1)) * K + k];
-            }
-            if (lane < nsel && t0 + lane < cap) {
-                const int p = p0 + (int)__fns(wd, 0, lane + 1);
-                const int y = p / W;
-                xy[(size_t)b * cap + t0 + lane] = make_float2((float)(p - y * W), (float)y);
-            }
-            __syncwarp();
-        }
-        return;
-    }
     if (w < nwords) {
         uint32_t word = bits[(size_t)b * nwords + w];
         int o = wordoff[(size_t)b * nwords + w];
@@ -420,10 +371,9 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
 }
 
 // ---------------------------------------------------------------------------------
-// gather access pattern for an interleaved vertex tensor ([..,K,2] contiguous) in DEVICE memory: 0 = auto (span walk when
-// the image is contiguous and the selection keeps >= 1/5 of the foreground, else pixel-wise), 1 = pixel-wise (one lane per
-// pixel, K independent loads in flight per lane), 2 = row-wise (consecutive lanes read consecutive float2 of one pixel's
-// 8*K-byte row), 3 = span walk wherever the layout allows it.  Measured on B200 at cfg-2 (profiles/r02_gather_modes.txt): select stage 60.6 us pixel-wise,
+// gather access pattern for an interleaved vertex tensor ([..,K,2] contiguous) in DEVICE memory: 0 = auto = 1 = pixel-wise
+// (one lane per pixel, K independent loads in flight per lane), 2 = row-wise (consecutive lanes read consecutive float2 of
+// one pixel's 8*K-byte row).  Measured on B200 at cfg-2 (profiles/r02_gather_modes.txt): select stage 60.6 us pixel-wise,
 // 71.1 us row-wise -- the kernel is latency-bound and the pixel-wise walk keeps 9 loads per lane in flight.  Pinned HOST
 // memory read in place is always fetched row-wise (a PCIe read is charged per 128-byte line touched, tools/pcie_probe.cu).
 // Tooling / A-B measurements; results are identical.
@@ -482,13 +432,9 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
     if (e != cudaSuccess) return e;
     dim3 g3(a.nblocks, a.B);
     const int gmode = g_gather_mode.load(std::memory_order_relaxed);
-    size_t smem = sizeof(unsigned short) * TS_THREADS * 32;                       // s_list
-    if (a.K <= GA_SPAN_MAX_K) smem = std::max(smem, (size_t)(GA_THREADS / 32) * 32 * a.K * sizeof(float2));
-    if (smem > 48 * 1024) return cudaErrorInvalidValue;                             // cannot happen for K <= GA_SPAN_MAX_K
-    gather_kernel<<<g3, GA_THREADS, smem, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
+    gather_kernel<<<g3, GA_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
                                                 a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
-                                                a.nblocks, a.K, a.cap, a.W, (a.rowwise_gather || gmode == 2) ? 1 : 0,
-                                                a.nz, a.H * a.W, gmode);
+                                                a.nblocks, a.K, a.cap, a.W, (a.rowwise_gather || gmode == 2) ? 1 : 0);
     return cudaGetLastError();
 }
 

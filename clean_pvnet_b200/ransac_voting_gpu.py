@@ -74,6 +74,29 @@ def _check_inputs(mask, vertex):
     return mask, vertex
 
 
+_desc_cache = {}
+
+
+def _cached_desc(lib, mask, vertex, hn, inlier_thresh, min_num, max_num, select_mode, seed, img_base, capacity):
+    """(descriptor, workspace bytes) for this problem shape; only seed / img_base change between calls of a steady loop,
+    so the ctypes struct and the layout query are built once per shape (the host side of a call stays ~50 us)."""
+    key = (mask.dtype, mask.stride(), tuple(vertex.shape), vertex.stride(), hn, float(inlier_thresh), min_num, max_num,
+           select_mode, capacity)
+    hit = _desc_cache.get(key)
+    if hit is None:
+        d = _make_desc(mask, vertex, hn, inlier_thresh, min_num, max_num, select_mode, 0, 0, capacity)
+        nbytes = lib.pvb_workspace_bytes(d)
+        if nbytes == 0:
+            _lib.check(lib.pvb_workspace_layout(d, _lib.PvbLayout()))
+        if len(_desc_cache) > 64:
+            _desc_cache.clear()
+        hit = _desc_cache[key] = (d, nbytes)
+    d, nbytes = hit
+    d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.img_base = int(img_base)
+    return d, nbytes
+
+
 def _make_desc(mask, vertex, hn, inlier_thresh, min_num, max_num, select_mode, seed, img_base, capacity):
     d = _lib.PvbDesc()
     d.B, d.H, d.W, d.K = vertex.size(0), vertex.size(1), vertex.size(2), vertex.size(3)
@@ -186,10 +209,7 @@ def _run(op, mask, vertex, hn, inlier_thresh, min_num, max_num, mean=None, idxs=
             need = H * W if selection is not None else min(H * W, int(max_num + 8 * math.sqrt(max(max_num, 0)) + 64))
             if int(capacity) < need:
                 raise RuntimeError(f"capacity={capacity} cannot hold the selection (needs >= {need}; H*W is always safe)")
-        d = _make_desc(mask, vertex, hn, inlier_thresh, min_num, max_num, select_mode, seed, img_base, capacity)
-        nbytes = lib.pvb_workspace_bytes(d)
-        if nbytes == 0:
-            _lib.check(lib.pvb_workspace_layout(d, _lib.PvbLayout()))
+        d, nbytes = _cached_desc(lib, mask, vertex, hn, inlier_thresh, min_num, max_num, select_mode, seed, img_base, capacity)
         ws = _workspace(dev, nbytes)
         stream = torch.cuda.current_stream(dev).cuda_stream
         ip = idxs.data_ptr() if idxs is not None else None

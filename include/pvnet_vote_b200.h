@@ -278,11 +278,9 @@ enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_COUNT = 4 };
 PVB_API int pvb_profile_enable(int32_t on);
 /* Tuning switches (tooling for A/B measurements; process-wide, atomic).  Results do not depend on them.
- *   gather_mode  access pattern of the gather kernel on an interleaved vertex tensor in device memory: 0 = auto (span walk
- *                -- stream the whole 32-pixel span of every bitmap word with a selected pixel through shared memory --
- *                when the image is contiguous and the selection keeps >= 1/5 of the foreground, else pixel-wise),
- *                1 = pixel-wise (one lane per pixel), 2 = row-wise (a warp reads whole 8*K-byte pixel rows; what
- *                in-place host reads always use), 3 = span walk wherever the layout allows
+ *   gather_mode  access pattern of the gather kernel on an interleaved vertex tensor in device memory: 0 = auto = 1 =
+ *                pixel-wise (one lane per pixel), 2 = row-wise (a warp reads whole 8*K-byte pixel rows; what in-place
+ *                host reads always use)
  *   vote_variant pixel tile of the vote kernel: 0 = 1 = 512 pixels (default), 2 = 256, 3 = 1024 */
 PVB_API int pvb_set_tuning(int32_t gather_mode, int32_t vote_variant);
 PVB_API int pvb_profile_reset(void);

@@ -331,13 +331,13 @@ def test_full_size_counts_against_reference_formulation(pvb):
 @pytest.mark.parametrize("H,W,K,max_num,layout", [
     (48, 64, 3, 30000, "interleaved"),      # whole words, no thinning: every foreground pixel selected
     (37, 53, 4, 30000, "interleaved"),      # H*W = 1961: the image ends inside a bitmap word
-    (37, 53, 5, 200, "interleaved"),        # thinned to ~200 of ~600: span walk in auto mode (keeps >= 1/5)
-    (96, 128, 9, 150, "interleaved"),       # keeps < 1/5: auto mode stays pixel-wise, mode 3 forces the span walk
-    (48, 64, 3, 30000, "planar"),           # strided NCHW view: the span walk does not apply, every mode falls back
+    (37, 53, 5, 200, "interleaved"),        # thinned to ~200 of ~600
+    (96, 128, 9, 150, "interleaved"),       # thinned hard
+    (48, 64, 3, 30000, "planar"),           # strided NCHW view: the row-wise walk does not apply and falls back
 ])
 def test_every_gather_walk_gives_the_same_compaction(pvb, H, W, K, max_num, layout):
-    """The gather kernel's access patterns (include/pvnet_vote_b200.h, pvb_set_tuning gather_mode): pixel-wise, row-wise,
-    span walk and the automatic choice must produce bit-identical xy / dirs / keypoints."""
+    """The gather kernel's access patterns (include/pvnet_vote_b200.h, pvb_set_tuning gather_mode): pixel-wise, row-wise
+    (what in-place host reads use) and the automatic choice must produce bit-identical xy / dirs / keypoints."""
     from clean_pvnet_b200 import _lib, synth
     lib = _lib.load()
     cfg = dict(B=3, H=H, W=W, K=K, hn=32, fill=(0.25, 0.4), kind="blob")
@@ -345,7 +345,7 @@ def test_every_gather_walk_gives_the_same_compaction(pvb, H, W, K, max_num, layo
     mask[2, H - 1, W - 3:] = 1                                   # foreground in the very last (partial) word
     ref = None
     try:
-        for mode in (1, 2, 3, 0):
+        for mode in (1, 2, 0):
             _lib.check(lib.pvb_set_tuning(mode, 0))
             out, dbg = pvb.ransac_voting_layer_v3(mask, vertex, 32, inlier_thresh=0.99, seed=5, max_num=max_num, debug=True)
             tn = dbg["tn"].tolist()                               # entries past tn are never written by any walk

@@ -15,7 +15,7 @@ ap.add_argument("--cfg", default="cfg2")
 ap.add_argument("--hn", type=int, default=512)
 ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--B", type=int, default=None)
-ap.add_argument("--chunks", default="0", help="gather modes (pvb_set_tuning): 0 auto, 1 pixel-wise, 2 row-wise, 3 span walk")
+ap.add_argument("--chunks", default="0", help="gather modes (pvb_set_tuning): 0 auto, 1 pixel-wise, 2 row-wise")
 ap.add_argument("--variants", default="0,1")
 args = ap.parse_args()
 lib = _lib.load()

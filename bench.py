@@ -60,9 +60,12 @@ def _env_int(name, default):
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.01):
-        self.index, self.period = index, period
+    def __init__(self, index, period=0.01, reasons_every=1, clock=True):
+        # every NVML query stalls the GPU it asks about (tools/scale_diag.py: clock + reasons at 100 Hz cost 31 us per
+        # 0.65 ms step), so the sampler asks as rarely as the contract allows: see run_ours()
+        self.index, self.period, self.reasons_every, self.clock = index, period, max(1, int(reasons_every)), clock
         self.samples, self.reasons = [], set()
+        self.reason_samples = 0
         self.max_mhz = None
         self._stop = threading.Event()
         self._thr = None
@@ -90,19 +93,25 @@ class ClockSampler:
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
+        it = 0
+        self._stop.wait(min(0.002, self.period))      # first sample 2 ms into the region: the GPU is under load by then
         while not self._stop.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                if self.clock:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                if it % self.reasons_every == 0:
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.reason_samples += 1
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(self.period)
+            it += 1
+            self._stop.wait(self.period)
 
     def start(self):
         if self.nv is not None:
@@ -117,7 +126,7 @@ class ClockSampler:
             return None
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "reason_samples": self.reason_samples, "period_ms": self.period * 1e3}
 
 
 def _peaks():
@@ -252,13 +261,16 @@ def run_ours(args):
         step(i)
     drain()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    # NVML polling is free with one process (tools/scale_diag.py at N=1: +1 us/step at 100 Hz) but 8 processes polling at
+    # 100 Hz cost every rank 31 us per 0.65 ms step (profiles/r02_scale_diag_n8.txt): rank 0 samples its GPU, the others do not
+    sampler = ClockSampler(local) if rank == 0 else None
     lib.pvb_profile_reset()
-    lib.pvb_profile_enable(1)
+    lib.pvb_profile_enable(args.profile_every)     # stage events on every n-th step only: each record drains the pipeline
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     last = None
@@ -272,7 +284,7 @@ def run_ours(args):
     out = gathered if gathered is not None else last
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     # ---- outside the timed region: the gathered result is what N single-GPU calls produce
     gather_check = None
     if layer is not None:
@@ -350,9 +362,12 @@ def run_ours(args):
         # the same tail as ONE launch straight from the fp32 outputs (pvb_uncertainty_pnp_from_votes), same initial pose ...
         extras["un_pnp_tail_fused_ms"] = timed(
             lambda: pvb.uncertainty_pnp_from_votes(kp2d, var, model, cam, init), 20)
-        # ... and with the reference's P3P initialisation computed inside the launch (no init_rt)
-        extras["un_pnp_tail_fused_p3p_ms"] = timed(
-            lambda: pvb.uncertainty_pnp_from_votes(kp2d, var, model, cam), 20)
+        # ... and the evaluator's real recipe, P3P initial pose included: three entry points vs one launch
+        def three_step():
+            w = pvb.uncertainty_pnp_weights(var)
+            return pvb.uncertainty_pnp_batch(kp2d, w, model, cam, pvb.p3p_init_batch(kp2d, w, model, cam))
+        extras["un_pnp_tail_p3p_3calls_ms"] = timed(three_step, 20)
+        extras["un_pnp_tail_p3p_fused_ms"] = timed(lambda: pvb.uncertainty_pnp_from_votes(kp2d, var, model, cam), 20)
     except Exception as e:
         extras["un_pnp_error"] = str(e)
 
@@ -442,7 +457,8 @@ def run_ours(args):
                     "sass_instr_per_test": 7.1,
                     "note": ("454 SASS instr per 16 pixels x 4 hypotheses per thread (256 FFMA, 64 FADD, 64 LEA.HI, 32 FMNMX3, "
                              "24 LDS); tools/microbench.cu bounds this mix at 610 cycles/block/SMSP => ~4.2 T tests/s")},
-            "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3]},
+            "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3],
+                          "profiled_steps": calls, "note": f"CUDA events at the stage boundaries of every {args.profile_every}-th timed step"},
             "host": {"enqueue_ms_per_step": (t_host1 - t_host0) * 1e3 / args.steps, "usable_cores": _usable_cores(),
                      "note": "host time spent enqueueing one step (rank 0); if it approaches ms_per_step the GPU is launch-starved"},
             "extras": extras,
@@ -561,6 +577,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=4, help="images per H2D chunk of the end-to-end path")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-every", type=int, default=4,
+                    help="record the stage events (stages_ms, roofline.kernel_ms) on every n-th timed step")
     ap.add_argument("--quick", action="store_true",
                     help="profiling passes (ncu): timed steps only -- no extras, no end-to-end runs, no CPU baseline")
     ap.add_argument("--traffic", type=float, default=None,

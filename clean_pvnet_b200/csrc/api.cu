@@ -31,11 +31,14 @@ int cuda_fail(cudaError_t e, const char *what)
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // ---- stage timing (pvb_profile_*) --------------------------------------------------------
+// stage i runs between boundary events ev[i] and ev[i+1] (5 records per profiled call: every event record is a
+// pipeline drain between two kernels, ~3 us each on B200, so the profile costs as little as it can and can be sampled)
 struct ProfCall {
-    cudaEvent_t start[PVB_STAGE_COUNT], end[PVB_STAGE_COUNT];   // per stage; stages may run on different streams
+    cudaEvent_t ev[PVB_STAGE_COUNT + 1];
     bool head;                                                   // first piece of an API call
 };
-thread_local bool g_prof_on = false;
+thread_local int g_prof_every = 0;          // 0: off; n: profile every n-th call
+thread_local unsigned g_prof_tick = 0;
 thread_local std::vector<ProfCall> g_prof_calls;
 thread_local std::vector<cudaEvent_t> g_prof_pool;
 
@@ -49,17 +52,17 @@ cudaEvent_t prof_event()
 
 ProfCall *prof_begin(bool head)
 {
-    if (!g_prof_on) return nullptr;
+    if (g_prof_every <= 0 || (g_prof_tick++ % (unsigned)g_prof_every) != 0) return nullptr;
     ProfCall pc;
-    for (auto &e : pc.start) e = prof_event();
-    for (auto &e : pc.end) e = prof_event();
+    for (auto &e : pc.ev) e = prof_event();
     pc.head = head;
     g_prof_calls.push_back(pc);
     return &g_prof_calls.back();
 }
 
-inline void prof_start(ProfCall *pc, int stage, cudaStream_t st) { if (pc) cudaEventRecord(pc->start[stage], st); }
-inline void prof_end(ProfCall *pc, int stage, cudaStream_t st) { if (pc) cudaEventRecord(pc->end[stage], st); }
+// stage boundaries: prof_start(stage 0) opens the call, prof_end(stage i) closes stage i and opens stage i+1
+inline void prof_start(ProfCall *pc, int stage, cudaStream_t st) { if (pc && stage == 0) cudaEventRecord(pc->ev[0], st); }
+inline void prof_end(ProfCall *pc, int stage, cudaStream_t st) { if (pc) cudaEventRecord(pc->ev[stage + 1], st); }
 
 int default_capacity(const pvb_desc *d)
 {
@@ -624,7 +627,7 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
     return PVB_OK;
 }
 
-PVB_API int pvb_profile_enable(int32_t on) { g_prof_on = on != 0; return PVB_OK; }
+PVB_API int pvb_profile_enable(int32_t every) { g_prof_every = every < 0 ? 0 : every; g_prof_tick = 0; return PVB_OK; }
 
 PVB_API int pvb_set_tuning(int32_t gather_mode, int32_t vote_variant)
 {
@@ -637,10 +640,8 @@ PVB_API int pvb_set_tuning(int32_t gather_mode, int32_t vote_variant)
 
 PVB_API int pvb_profile_reset(void)
 {
-    for (auto &pc : g_prof_calls) {
-        for (auto e : pc.start) g_prof_pool.push_back(e);
-        for (auto e : pc.end) g_prof_pool.push_back(e);
-    }
+    for (auto &pc : g_prof_calls)
+        for (auto e : pc.ev) g_prof_pool.push_back(e);
     g_prof_calls.clear();
     return PVB_OK;
 }
@@ -651,9 +652,9 @@ PVB_API int pvb_profile_read(double *ms, int32_t n)
     int calls = 0;
     for (auto &pc : g_prof_calls) {
         for (int i = 0; i < PVB_STAGE_COUNT; ++i) {
-            cudaError_t e = cudaEventSynchronize(pc.end[i]);
+            cudaError_t e = cudaEventSynchronize(pc.ev[i + 1]);
             float t = 0.f;
-            if (e == cudaSuccess) e = cudaEventElapsedTime(&t, pc.start[i], pc.end[i]);
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&t, pc.ev[i], pc.ev[i + 1]);
             if (e != cudaSuccess) { cuda_fail(e, "profile elapsed"); return -1; }
             ms[i] += (double)t;
         }

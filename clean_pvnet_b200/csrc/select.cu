@@ -358,6 +358,8 @@ gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff
         xy[(size_t)b * cap + t] = make_float2((float)x, (float)y);
         const float *vb = vimg + (long long)y * sH + (long long)x * sW;
         float2 *db = dirs + (size_t)b * K * cap + t;
+        // plain cached loads: the K loads of one pixel hit the same one or two lines, and an evict-first hint
+        // (ld.global.cs) throws those lines out between them -- measured +19 us on the select stage (profiles/r02_scale_diag_n1.txt)
         if (vec) {
             for (int k = 0; k < K; ++k)
                 db[(size_t)k * cap] = __ldg(reinterpret_cast<const float2 *>(vb + (long long)k * sK));

@@ -364,6 +364,7 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__res
     __shared__ int s_last, s_final;
     // Exactly one CTA per (image, keypoint) writes out[bk]: CTA 0 of a skipped image, otherwise the CTA that draws the
     // last ticket.  Only those CTAs reach the exchange tail at the bottom.
+    float2 res = make_float2(0.f, 0.f);   // this (image, keypoint)'s result, held by thread 0 of the CTA that writes it
     if (a.state[b] != 0 || tn <= 0) {   // :129-132 -> zeros
         if (split != 0) return;
         if (tid == 0) { out[bk * 2] = 0.f; out[bk * 2 + 1] = 0.f; win[bk] = make_float2(0.f, 0.f); }
@@ -439,24 +440,24 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__res
             if (det == 0.0 || !isfinite(det)) { x = (float)s[3]; y = (float)s[4]; }   // b_inv's identity fallback (:105-108)
             else { x = (float)((s[2] * s[3] - s[1] * s[4]) / det); y = (float)((s[0] * s[4] - s[1] * s[3]) / det); }
             out[bk * 2] = x; out[bk * 2 + 1] = y;
+            res = make_float2(x, y);
         }
     }
-    // ---- exchange tail (multi-GPU): the writer of the call's LAST result pushes the whole [B][K][2] block to every peer
+    // ---- exchange tail (multi-GPU).  Every writer stores ITS 8 bytes straight into every peer's receive slot over NVLink
+    // (r == own rank: local), fences at system scope and counts itself in; the writer that completes the call publishes
+    // `seq` in the peers' flag words.  Causality: peer store -> fence.sys -> atomic (observed by the last writer) ->
+    // fence.sys -> flag store (release) -> the consumer's acquire load: a rank that sees the flag sees all B*K results.
+    // The stores of the 144 writers overlap each other and the refit work still running; only the last fence and the flag
+    // stores sit on the kernel's tail.
     if (pp.world <= 0) return;
     if (tid == 0) {
-        __threadfence();                                                   // out[bk] before the arrival count
+        for (int r = 0; r < pp.world; ++r) reinterpret_cast<float2 *>(pp.recv[r])[bk] = res;
+        __threadfence_system();
         s_final = (atomicAdd(pp.done, 1) == a.B * a.K - 1);
+        if (s_final) __threadfence_system();
     }
     __syncthreads();
-    if (!s_final) return;
-    __threadfence();                                                       // every other writer's out[] is visible now
-    for (int i = tid; i < pp.nfloats; i += RF_THREADS) {
-        const float v = __ldcg(out + i);
-        for (int r = 0; r < pp.world; ++r) pp.recv[r][i] = v;              // peer stores over NVLink (r == own rank: local)
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < pp.world)                                                    // data first (fence above), then the flag
+    if (s_final && tid < pp.world)
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[tid]), "l"(pp.seq) : "memory");
 }
 

@@ -267,16 +267,17 @@ PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, double 
 PVB_API int pvb_exchange_status(pvb_exchange *ex, pvb_stream_t stream); /* synchronises; PVB_ERR_TIMEOUT after a timed-out wait */
 PVB_API int pvb_exchange_destroy(pvb_exchange *ex);
 
-/* Stage timing (tooling, used by bench.py).  When enabled, the layer entry points record CUDA
- * events on the launching stream around each stage; pvb_profile_read() synchronises those events
- * and ADDS the elapsed milliseconds of every call since the last pvb_profile_reset() into
- * ms[PVB_STAGE_COUNT], returning the number of calls accumulated.  Per host thread. */
+/* Stage timing (tooling, used by bench.py).  pvb_profile_enable(n): n = 0 off; n >= 1: every n-th call of a layer entry
+ * point records 5 CUDA events on the launching stream at its stage boundaries (an event record drains the pipeline between
+ * two kernels, ~3 us each on B200: sample with n > 1 to keep the profile out of a measurement).  pvb_profile_read()
+ * synchronises those events and ADDS the elapsed milliseconds of every profiled call since the last pvb_profile_reset()
+ * into ms[PVB_STAGE_COUNT], returning the number of calls accumulated.  Per host thread. */
 enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
        PVB_STAGE_GENERATE = 1, /* hypothesis generation */
        PVB_STAGE_VOTE = 2,     /* counts memset + vote kernel (the dominant kernel) */
        PVB_STAGE_FINISH = 3,   /* winner + refit, or covariance */
        PVB_STAGE_COUNT = 4 };
-PVB_API int pvb_profile_enable(int32_t on);
+PVB_API int pvb_profile_enable(int32_t every);
 /* Tuning switches (tooling for A/B measurements; process-wide, atomic).  Results do not depend on them.
  *   gather_mode  access pattern of the gather kernel on an interleaved vertex tensor in device memory: 0 = auto = 1 =
  *                pixel-wise (one lane per pixel), 2 = row-wise (a warp reads whole 8*K-byte pixel rows; what in-place

@@ -29,7 +29,7 @@ layer = parallel.ShardedVotingLayer(B * world, K, depth=4, device=dev) if world 
 STEPS = 60
 
 
-def loop(exchange, sampler_period, profile):
+def loop(exchange, sampler_period, profile, reasons_every=1, clock=True):
     def step(i):
         if exchange and layer is not None:
             return layer(mask, vertex, HN, inlier_thresh=0.99, seed=1000 + i)
@@ -39,7 +39,7 @@ def loop(exchange, sampler_period, profile):
     if layer is not None:
         layer.drain()
     torch.cuda.synchronize()
-    smp = bench.ClockSampler(local, period=sampler_period) if sampler_period else None
+    smp = bench.ClockSampler(local, period=sampler_period, reasons_every=reasons_every, clock=clock) if sampler_period else None
     lib.pvb_profile_reset()
     lib.pvb_profile_enable(1 if profile else 0)
     if world > 1:
@@ -78,9 +78,14 @@ variants = [("exchange + sampler 10ms + profile (bench default)", True, 0.01, Tr
             ("exchange only", True, 0, False),
             ("plain v3 (no exchange), nothing else", False, 0, False),
             ("plain v3 + profile", False, 0, True),
-            ("exchange + sampler 100ms + profile", True, 0.1, True)]
-for name, ex, per, prof in variants:
-    r = loop(ex, per, prof)
+            ("exchange + sampler 100ms + profile", True, 0.1, True),
+            ("plain v3 + sampler 10ms (clock + reasons)", False, 0.01, False),
+            ("plain v3 + sampler 10ms, clock only", False, 0.01, False, 10 ** 9, True),
+            ("plain v3 + sampler 10ms, reasons only", False, 0.01, False, 1, False),
+            ("plain v3 + sampler 2ms (clock + reasons)", False, 0.002, False)]
+for v in variants:
+    name, ex, per, prof = v[:4]
+    r = loop(ex, per, prof, *v[4:])
     if rank == 0:
         print(f"{name:52s} ms/step max {r[:, 0].max():.4f} (rank0 {r[0, 0]:.4f})  host enqueue ms/step max {r[:, 1].max():.4f}  "
               f"select us per rank {[round(float(x) * 1e3, 1) for x in r[:, 2]]}  vote us rank0 {float(r[0, 3]) * 1e3:.1f}", flush=True)

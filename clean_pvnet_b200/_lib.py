@@ -34,7 +34,7 @@ class PvbDesc(ctypes.Structure):
 class PvbLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in
                 ("total", "status", "fgsum", "nz", "tn", "state", "bits", "wordoff", "blocktot", "xy", "dirs", "hyp",
-                 "counts", "win", "refit_partial", "refit_ticket", "refit_done")] + [
+                 "counts", "win", "refit_partial", "refit_ticket")] + [
                     ("nwords", ctypes.c_int32), ("nblocks", ctypes.c_int32), ("capacity", ctypes.c_int32),
                     ("refit_splits", ctypes.c_int32)]
 
@@ -73,7 +73,7 @@ SIGNATURES = {
     "pvb_exchange_connect": (ctypes.c_int, [_vp, _vp]),
     "pvb_exchange_connect_ptrs": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_void_p)]),
     "pvb_ransac_voting_v3_push": (ctypes.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, ctypes.c_uint64, _vp]),
-    "pvb_exchange_wait": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, ctypes.c_double, _vp]),
+    "pvb_exchange_wait": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _vp, ctypes.c_double, _vp]),
     "pvb_exchange_status": (ctypes.c_int, [_vp, _vp]),
     "pvb_exchange_destroy": (ctypes.c_int, [_vp]),
     "pvb_profile_enable": (ctypes.c_int, [_i32]),

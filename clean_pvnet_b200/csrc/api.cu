@@ -109,7 +109,6 @@ int make_layout(const pvb_desc *d, pvb_layout *L)
     L->tn = take(B * sizeof(int));
     L->state = take(B * sizeof(int));
     L->refit_ticket = take(B * K * sizeof(int));
-    L->refit_done = take(sizeof(int));
     L->bits = take(B * nwords * sizeof(uint32_t));
     L->wordoff = take(B * nwords * sizeof(int));
     L->blocktot = take(B * nblocks * sizeof(int));
@@ -133,7 +132,6 @@ struct Plan {
     VoteArgs v;
     float2 *win;
     RefitScratch refit;
-    int *done;            // results written by the refit kernel (exchange tail)
 };
 
 int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
@@ -180,13 +178,12 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     P->refit.partial = reinterpret_cast<double *>(w + L.refit_partial);
     P->refit.ticket = reinterpret_cast<int *>(w + L.refit_ticket);
     P->refit.splits = L.refit_splits;
-    P->done = reinterpret_cast<int *>(w + L.refit_done);
     return PVB_OK;
 }
 
 int run_select(const Plan &P, cudaStream_t st)
 {
-    // status, fgsum, nz, tn, state, refit tickets, refit_done: contiguous at the start of the workspace
+    // status, fgsum, nz, tn, state, refit tickets: contiguous at the start of the workspace
     cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.bits, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(header)");
     e = launch_select(P.s, st);
@@ -216,8 +213,8 @@ int run_front(const Plan &P, cudaStream_t st, ProfCall *pc)
 
 struct pvb_exchange {
     int rank, world, slots, device;
-    size_t bytes_per_rank;      // 16-byte multiple
-    size_t flags_off, status_off, total;
+    size_t bytes_per_rank;      // payload bytes per rank and call (a multiple of 16); the ring holds 2x (8-byte words)
+    size_t status_off, total;
     char *local;                // this rank's ring (cudaMalloc)
     char *peer[PVB_MAX_PEERS];  // every rank's ring as seen from this device (peer[rank] == local)
     bool ipc_opened[PVB_MAX_PEERS];
@@ -226,22 +223,19 @@ struct pvb_exchange {
 
 namespace {
 
-int exchange_push_args(pvb_exchange *ex, uint64_t seq, size_t nbytes, int *done, PeerPush *pp)
+int exchange_push_args(pvb_exchange *ex, uint64_t seq, size_t nbytes, PeerPush *pp)
 {
     memset(pp, 0, sizeof(*pp));
     if (!ex) return PVB_OK;
     if (!ex->connected) return fail(PVB_ERR_INVALID, "exchange is not connected (pvb_exchange_connect*)");
-    if (seq == 0) return fail(PVB_ERR_INVALID, "seq must be >= 1");
+    if (seq == 0 || (uint32_t)seq == 0) return fail(PVB_ERR_INVALID, "seq must be >= 1 and not a multiple of 2^32");
     if (nbytes > ex->bytes_per_rank) return fail(PVB_ERR_INVALID, "result block (%zu bytes) exceeds the exchange's bytes_per_rank (%zu)", nbytes, ex->bytes_per_rank);
     const size_t slot = (size_t)((seq - 1) % (uint64_t)ex->slots);
+    const size_t words = ex->bytes_per_rank / sizeof(float);             // 8-byte words per rank and slot
     pp->world = ex->world;
-    pp->nfloats = (int)(nbytes / sizeof(float));
-    pp->seq = seq;
-    pp->done = done;
-    for (int r = 0; r < ex->world; ++r) {
-        pp->recv[r] = reinterpret_cast<float *>(ex->peer[r] + (slot * ex->world + ex->rank) * ex->bytes_per_rank);
-        pp->flag[r] = reinterpret_cast<unsigned long long *>(ex->peer[r] + ex->flags_off) + slot * ex->world + ex->rank;
-    }
+    pp->seq = (uint32_t)seq;
+    for (int r = 0; r < ex->world; ++r)
+        pp->recv[r] = reinterpret_cast<uint2 *>(ex->peer[r]) + (slot * ex->world + ex->rank) * words;
     return PVB_OK;
 }
 
@@ -284,7 +278,7 @@ static int run_v3(const pvb_desc *d, const void *mask, const float *vertex, cons
     if (rc) return rc;
     if (!out_kpt) return fail(PVB_ERR_INVALID, "out_kpt is NULL");
     PeerPush pp;
-    rc = exchange_push_args(ex, seq, (size_t)d->B * d->K * 2 * sizeof(float), P.done, &pp);
+    rc = exchange_push_args(ex, seq, (size_t)d->B * d->K * 2 * sizeof(float), &pp);
     if (rc) return rc;
     if (d->B == 0) {
         if (pp.world > 0) return fail(PVB_ERR_INVALID, "an exchanging call needs B >= 1 on every rank");
@@ -772,8 +766,7 @@ PVB_API int pvb_exchange_create(int32_t rank, int32_t world, int32_t slots, size
     memset(ex, 0, sizeof(*ex));
     ex->rank = rank; ex->world = world; ex->slots = slots;
     ex->bytes_per_rank = (bytes_per_rank + 15) / 16 * 16;
-    ex->flags_off = align_up((size_t)slots * world * ex->bytes_per_rank);
-    ex->status_off = align_up(ex->flags_off + (size_t)slots * world * sizeof(unsigned long long));
+    ex->status_off = align_up((size_t)slots * world * ex->bytes_per_rank * 2);      // ring of {float bits, seq} words
     ex->total = ex->status_off + 256;
     cudaError_t e = cudaGetDevice(&ex->device);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ex->local), ex->total);
@@ -830,16 +823,24 @@ PVB_API int pvb_exchange_connect(pvb_exchange *ex, const void *handles)
     return PVB_OK;
 }
 
-PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, double timeout_s, pvb_stream_t stream)
+PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, const int32_t *floats_per_rank, double timeout_s,
+                              pvb_stream_t stream)
 {
     if (!ex || !out) return fail(PVB_ERR_INVALID, "NULL argument");
-    if (seq == 0) return fail(PVB_ERR_INVALID, "seq must be >= 1");
-    if (reinterpret_cast<uintptr_t>(out) & 15u) return fail(PVB_ERR_INVALID, "out must be 16-byte aligned");
+    if (seq == 0 || (uint32_t)seq == 0) return fail(PVB_ERR_INVALID, "seq must be >= 1 and not a multiple of 2^32");
+    if (reinterpret_cast<uintptr_t>(out) & 3u) return fail(PVB_ERR_INVALID, "out must be 4-byte aligned");
     if (!(timeout_s > 0.0)) timeout_s = 10.0;
+    const int words = (int)(ex->bytes_per_rank / sizeof(float));
+    ExchangeCounts counts;
+    for (int r = 0; r < PVB_MAX_PEERS; ++r) counts.n[r] = 0;
+    for (int r = 0; r < ex->world; ++r) {
+        const int n = floats_per_rank ? floats_per_rank[r] : words;
+        if (n < 0 || n > words) return fail(PVB_ERR_INVALID, "floats_per_rank[%d] = %d outside [0, %d]", r, n, words);
+        counts.n[r] = n;
+    }
     const size_t slot = (size_t)((seq - 1) % (uint64_t)ex->slots);
-    const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(ex->local + ex->flags_off) + slot * ex->world;
-    const char *recv = ex->local + slot * ex->world * ex->bytes_per_rank;
-    cudaError_t e = launch_exchange_wait(flags, seq, recv, out, (size_t)ex->world * ex->bytes_per_rank / 16, ex->world,
+    const uint2 *recv = reinterpret_cast<const uint2 *>(ex->local) + slot * ex->world * words;
+    cudaError_t e = launch_exchange_wait(recv, (uint32_t)seq, static_cast<float *>(out), ex->world, words, counts,
                                          (unsigned long long)(timeout_s * 1e9), reinterpret_cast<int *>(ex->local + ex->status_off),
                                          static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? PVB_OK : cuda_fail(e, "exchange wait kernel");

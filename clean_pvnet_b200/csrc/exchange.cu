@@ -6,14 +6,17 @@
 // kernel (co-scheduled with the vote kernel, spinning until the slowest rank arrives) cost 0.30 ms of a 0.97 ms step.
 //
 // Here the exchange is part of the producing kernel: every rank owns a receive ring in its own HBM
-//     recv  [slots][world][bytes_per_rank]      flags uint64 [slots][world]
-// mapped into every peer (CUDA IPC, opened once).  The refit kernel's last CTA stores the rank's result block into slot
-// (seq-1) % slots of EVERY peer's ring -- plain stores that travel over NVLink/NVSwitch -- and then publishes `seq` in the
-// peers' flag words (vote.cu, "exchange tail").  Producers never wait.  A consumer that wants the gathered result of call
-// `seq` enqueues pvb_exchange_wait on its stream: one small CTA that polls its OWN HBM until all flags[slot][r] >= seq and
-// copies the slot out.  Ring reuse is made safe by the caller's schedule (clean_pvnet_b200/parallel.py: the wait of call
-// s-D is enqueued before call s, slots = 2*D), not by acknowledgements, so no kernel ever blocks on a peer's progress
-// except the wait kernel itself, and that one is bounded by a timeout.
+//     recv  uint2 [slots][world][floats_per_rank]        word = {float bits, seq}
+// mapped into every peer (CUDA IPC, opened once).  The thread of the refit kernel that produces an (image, keypoint) result
+// stores it into slot (seq-1) % slots of EVERY peer's ring as two 8-byte words -- plain stores that travel over
+// NVLink/NVSwitch (vote.cu, "exchange tail").  An aligned 8-byte store is single-copy atomic, so each word validates
+// itself (NCCL's LL protocol): no fence, no completion counter, no flag; producers never wait.  A consumer that wants the
+// gathered result of call `seq` enqueues pvb_exchange_wait on its stream: one small CTA that polls the words of its OWN
+// ring until all of them carry `seq`, and writes the floats out.  Ring reuse is made safe by the caller's schedule
+// (clean_pvnet_b200/parallel.py: the wait of call s-D is enqueued before call s, slots = 2*D), not by acknowledgements,
+// so no kernel ever blocks on a peer's progress except the wait kernel itself, and that one is bounded by a timeout.
+// (Round 2 first built this with a completion counter, a system-scope fence and per-rank flag words: the fence on the
+// kernel's tail cost 6 us per step, 15 us when every writer fenced -- profiles/r02_bench_n8_peer_fence_protocol.json.)
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -21,10 +24,10 @@
 
 namespace pvb {
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+__device__ __forceinline__ uint2 ld_word(const uint2 *p)
 {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 
@@ -38,36 +41,39 @@ __device__ __forceinline__ unsigned long long global_ns()
 constexpr int XW_THREADS = 128;
 
 __global__ void __launch_bounds__(XW_THREADS)
-exchange_wait_kernel(const unsigned long long *__restrict__ flags, unsigned long long seq, const uint4 *__restrict__ recv,
-                     uint4 *__restrict__ out, size_t n16, int world, unsigned long long timeout_ns, int *status)
+exchange_wait_kernel(const uint2 *__restrict__ recv, unsigned int seq, float *__restrict__ out, int world, int stride_words,
+                     ExchangeCounts counts, unsigned long long timeout_ns, int *status)
 {
     __shared__ int s_timed_out;
     const int tid = threadIdx.x;
     if (tid == 0) s_timed_out = 0;
     __syncthreads();
-    if (tid < world) {
-        const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(flags + tid) < seq) {
-            if (global_ns() - t0 > timeout_ns) { atomicExch(&s_timed_out, 1); break; }
-            __nanosleep(100);
+    const unsigned long long t0 = global_ns();
+    for (int r = 0; r < world; ++r) {
+        const uint2 *src = recv + (size_t)r * stride_words;
+        float *dst = out + (size_t)r * stride_words;
+        for (int i = tid; i < counts.n[r]; i += XW_THREADS) {
+            uint2 w = ld_word(src + i);
+            while (w.y != seq) {                             // the word has not arrived yet (it still carries an older seq)
+                if (global_ns() - t0 > timeout_ns) { atomicExch(&s_timed_out, 1); break; }
+                __nanosleep(100);
+                w = ld_word(src + i);
+            }
+            dst[i] = __uint_as_float(w.x);
         }
     }
     __syncthreads();
     if (s_timed_out) {
         if (tid == 0) atomicExch(status, 1);
-        const uint4 nan4 = make_uint4(0x7fc00000u, 0x7fc00000u, 0x7fc00000u, 0x7fc00000u);
-        for (size_t i = tid; i < n16; i += XW_THREADS) out[i] = nan4;
-        return;
+        for (int r = 0; r < world; ++r)
+            for (int i = tid; i < counts.n[r]; i += XW_THREADS) out[(size_t)r * stride_words + i] = __int_as_float(0x7fc00000);
     }
-    // the peers' stores were released before their flags; the acquire loads above order these reads after them
-    for (size_t i = tid; i < n16; i += XW_THREADS) out[i] = __ldcg(recv + i);
 }
 
-cudaError_t launch_exchange_wait(const unsigned long long *flags, unsigned long long seq, const void *recv, void *out,
-                                 size_t n16, int world, unsigned long long timeout_ns, int *status, cudaStream_t st)
+cudaError_t launch_exchange_wait(const uint2 *recv, unsigned int seq, float *out, int world, int stride_words,
+                                 const ExchangeCounts &counts, unsigned long long timeout_ns, int *status, cudaStream_t st)
 {
-    exchange_wait_kernel<<<1, XW_THREADS, 0, st>>>(flags, seq, static_cast<const uint4 *>(recv), static_cast<uint4 *>(out),
-                                                   n16, world, timeout_ns, status);
+    exchange_wait_kernel<<<1, XW_THREADS, 0, st>>>(recv, seq, out, world, stride_words, counts, timeout_ns, status);
     return cudaGetLastError();
 }
 

@@ -53,24 +53,25 @@ void set_gather_tuning(int mode);    // tooling: gather access pattern (select.c
 // them in a fixed order and solves, so the result is deterministic.
 struct RefitScratch { double *partial; int *ticket; int splits; };
 int refit_splits_for(int cap);
-// Multi-GPU result exchange fused into the refit kernel: the CTA that completes the LAST (image,keypoint) of
-// the call stores the rank's whole [B][K][2] result into every peer's receive slot over NVLink (plain peer stores) and then
-// publishes `seq` in every peer's flag word; nobody waits here (pvb_exchange_wait does, later, on the consumer's stream).
+// Multi-GPU result exchange fused into the refit kernel.  The thread that writes an (image, keypoint) result
+// also stores it into every peer's receive slot over NVLink as two 8-byte words {float bits, seq}: an aligned 8-byte
+// store is single-copy atomic, so the word carries its own validity flag (the protocol NCCL calls LL) and the producer
+// needs no fence, no completion counter and no separate flag -- it fires 2*world stores and is done.  Consumers poll the
+// words of slot (seq-1) % slots in their OWN memory until every flag equals seq (launch_exchange_wait).
 constexpr int PVB_MAX_PEERS = 16;
 struct PeerPush {
     int world;                                  // 0: no exchange
-    int nfloats;                                // B*K*2
-    unsigned long long seq;                     // value published in the flags (monotonic per exchange)
-    int *done;                                  // workspace counter, zeroed per call: (image,keypoint) results written
-    float *recv[PVB_MAX_PEERS];                 // peer r: where THIS rank's slice of the current slot lives in r's memory
-    unsigned long long *flag[PVB_MAX_PEERS];    // peer r: flag word of (current slot, this rank)
+    unsigned int seq;                           // low 32 bits of the call's sequence number (never 0)
+    uint2 *recv[PVB_MAX_PEERS];                 // peer r: where THIS rank's words of the current slot live in r's memory
 };
 cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, const PeerPush &pp,
                          cudaStream_t st);
-// spins (bounded by timeout_ns) until flags[r] >= seq for r < world, then copies n16 16-byte words recv -> out;
-// on timeout sets *status = 1 and fills `out` with NaN
-cudaError_t launch_exchange_wait(const unsigned long long *flags, unsigned long long seq, const void *recv, void *out,
-                                 size_t n16, int world, unsigned long long timeout_ns, int *status, cudaStream_t st);
+// polls the {data, seq} words of one slot -- rank r publishes counts.n[r] floats at recv + r*stride_words -- until every
+// flag equals seq (bounded by timeout_ns), writing the data to out[r*stride_words + i]; on timeout sets *status = 1 and
+// fills `out` with NaN
+struct ExchangeCounts { int n[PVB_MAX_PEERS]; };
+cudaError_t launch_exchange_wait(const uint2 *recv, unsigned int seq, float *out, int world, int stride_words,
+                                 const ExchangeCounts &counts, unsigned long long timeout_ns, int *status, cudaStream_t st);
 // ratio/threshold/weighted covariance -> out_cov [B][K][2][2]
 cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, cudaStream_t st);
 

@@ -361,7 +361,7 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__res
     const size_t bk = (size_t)b * a.K + k;
     __shared__ int s_c[NW], s_h[NW];
     __shared__ double s_acc[NW][5];
-    __shared__ int s_last, s_final;
+    __shared__ int s_last;
     // Exactly one CTA per (image, keypoint) writes out[bk]: CTA 0 of a skipped image, otherwise the CTA that draws the
     // last ticket.  Only those CTAs reach the exchange tail at the bottom.
     float2 res = make_float2(0.f, 0.f);   // this (image, keypoint)'s result, held by thread 0 of the CTA that writes it
@@ -443,22 +443,16 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__res
             res = make_float2(x, y);
         }
     }
-    // ---- exchange tail (multi-GPU).  Every writer stores ITS 8 bytes straight into every peer's receive slot over NVLink
-    // (r == own rank: local), fences at system scope and counts itself in; the writer that completes the call publishes
-    // `seq` in the peers' flag words.  Causality: peer store -> fence.sys -> atomic (observed by the last writer) ->
-    // fence.sys -> flag store (release) -> the consumer's acquire load: a rank that sees the flag sees all B*K results.
-    // The stores of the 144 writers overlap each other and the refit work still running; only the last fence and the flag
-    // stores sit on the kernel's tail.
-    if (pp.world <= 0) return;
-    if (tid == 0) {
-        for (int r = 0; r < pp.world; ++r) reinterpret_cast<float2 *>(pp.recv[r])[bk] = res;
-        __threadfence_system();
-        s_final = (atomicAdd(pp.done, 1) == a.B * a.K - 1);
-        if (s_final) __threadfence_system();
+    // ---- exchange tail (multi-GPU): the thread that produced this (image, keypoint) result stores it into every peer's
+    // receive slot over NVLink (r == own rank: local) as two self-validating 8-byte words {float bits, seq}.  Fire and
+    // forget: no fence, no counter, no flag (kernels.h, PeerPush).
+    if (pp.world <= 0 || tid != 0) return;
+    const uint2 wx = make_uint2(__float_as_uint(res.x), pp.seq), wy = make_uint2(__float_as_uint(res.y), pp.seq);
+    for (int r = 0; r < pp.world; ++r) {
+        uint2 *dst = pp.recv[r] + bk * 2;
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(wx.x), "r"(wx.y) : "memory");
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 1), "r"(wy.x), "r"(wy.y) : "memory");
     }
-    __syncthreads();
-    if (s_final && tid < pp.world)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[tid]), "l"(pp.seq) : "memory");
 }
 
 cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, const PeerPush &pp,

@@ -9,10 +9,11 @@ identical for any number of ranks.
 
 Two ways to make the results visible:
 
-  gather="peer" (default on GPUs)   the exchange is FUSED INTO THE REFIT KERNEL: its last CTA stores the rank's block
-      straight into every peer's receive ring over NVLink and publishes a flag (csrc/exchange.cu, vote.cu "exchange
-      tail").  Nothing waits in the producing call and no collective kernel is launched; a tiny wait kernel, enqueued
-      `depth` calls later (or when the result is asked for), polls the rank's OWN memory and copies the slot out.
+  gather="peer" (default on GPUs)   the exchange is FUSED INTO THE REFIT KERNEL: the thread that produces an (image,
+      keypoint) result stores it straight into every peer's receive ring over NVLink as self-validating 8-byte words
+      {float, seq} (csrc/exchange.cu, vote.cu "exchange tail"): no fence, no flag, nothing waits in the producing call and
+      no collective kernel is launched; a tiny wait kernel, enqueued `depth` calls later (or when the result is asked
+      for), polls the rank's OWN memory until every word carries the call's sequence number and writes the floats out.
       Round 1's per-call NCCL all_gather cost 0.30 ms of a 0.97 ms step at 8 GPUs (NCCL's kernel must become co-resident
       on all GPUs and spins holding SM slots until the slowest rank arrives); this path has no such rendezvous.
   gather="collective"               one torch.distributed all_gather per call (NCCL on GPUs, gloo in the CPU tests of the
@@ -115,9 +116,13 @@ class PeerExchange:
         self._lib_mod.check(self.lib.pvb_exchange_connect_ptrs(self.handle, arr))
         return self
 
-    def wait(self, seq, out, timeout_s=10.0):
-        """Enqueues the wait kernel of call `seq` on the current stream; `out` = uint8 [world*bytes_per_rank] on this device."""
-        self._lib_mod.check(self.lib.pvb_exchange_wait(self.handle, int(seq), out.data_ptr(), float(timeout_s),
+    def wait(self, seq, out, timeout_s=10.0, floats_per_rank=None):
+        """Enqueues the wait kernel of call `seq` on the current stream; `out` = uint8 [world*bytes_per_rank] on this device.
+        floats_per_rank: how many floats each rank publishes per call (ragged shards); None = bytes_per_rank/4 each."""
+        counts = None
+        if floats_per_rank is not None:
+            counts = (ctypes.c_int32 * self.world)(*[int(n) for n in floats_per_rank])
+        self._lib_mod.check(self.lib.pvb_exchange_wait(self.handle, int(seq), out.data_ptr(), counts, float(timeout_s),
                                                        torch.cuda.current_stream(self.device).cuda_stream))
 
     def check(self):
@@ -237,7 +242,7 @@ class ShardedVotingLayer:
             q = self.inflight.pop(0)
             if self.exchange is not None:
                 buf = torch.empty(self.world * self.exchange.bytes_per_rank, dtype=torch.uint8, device=self.device)
-                self.exchange.wait(q.seq, buf, self.timeout_s)
+                self.exchange.wait(q.seq, buf, self.timeout_s, [(hi - lo) * self.K * 2 for lo, hi in self.sizes])
                 rows = buf.view(self.world, self.exchange.bytes_per_rank)[:, : self.nmax * self.K * 8]
                 out = rows.reshape(self.world * self.nmax * self.K * 8).view(torch.float32).view(self.world * self.nmax, self.K, 2)
                 q._gathered = _unpad(out, self.sizes, self.nmax, (self.K, 2))

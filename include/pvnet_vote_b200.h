@@ -119,7 +119,6 @@ typedef struct pvb_layout {
     size_t win;      /* float2[B][K] winning hypothesis before the refit */
     size_t refit_partial; /* double[B][K][refit_splits][5] partial normal equations */
     size_t refit_ticket;  /* int32[B][K] arrival counters of the refit CTAs */
-    size_t refit_done;    /* int32 (image,keypoint) results written (multi-GPU push trigger) */
     int32_t nwords;  /* ceil(H*W/32) */
     int32_t nblocks; /* ceil(nwords/128) */
     int32_t capacity;
@@ -242,14 +241,16 @@ PVB_API int pvb_ransac_voting_v3_host(const pvb_desc *d, const void *mask_host, 
 /* ---- multi-GPU: images are sharded across ranks, one process per GPU --------------------------------
  * The path has no exchange inside the algorithm; what crosses GPUs is each rank's [B_r,K,2] keypoints becoming visible on
  * every rank.  The reference has no counterpart (torch.nn.DataParallel in the trainer only, lib/train/trainers/trainer.py:11).
- * A pvb_exchange is a receive ring in this rank's HBM -- recv[slots][world][bytes_per_rank] + one flag word per
- * (slot, rank) -- mapped into every peer through CUDA IPC.  pvb_ransac_voting_v3_push is pvb_ransac_voting_v3 whose refit
- * kernel ALSO stores the rank's result block into slot (seq-1)%slots of every peer's ring over NVLink and then publishes
- * `seq` in the peers' flag words; it never waits.  pvb_exchange_wait enqueues a one-CTA kernel that polls this rank's own
- * flags until all `world` ranks have published `seq` (bounded by timeout_s) and copies the slot to `out`
- * (device, [world][bytes_per_rank], 16-byte aligned).  Ring discipline (caller): before call `seq` is launched, the wait of
- * call `seq - slots/2` must already be enqueued on the same stream on every rank; seq starts at 1 and increases by 1 per
- * call on every rank alike.  Setup (once): create -> get_handle -> all-gather the 64-byte handles by any means (e.g.
+ * A pvb_exchange is a receive ring in this rank's HBM -- recv[slots][world][floats_per_rank] of 8-byte words
+ * {float bits, seq} -- mapped into every peer through CUDA IPC.  pvb_ransac_voting_v3_push is pvb_ransac_voting_v3 whose
+ * refit kernel ALSO stores every (image, keypoint) result, as it is produced, into slot (seq-1)%slots of every peer's ring
+ * over NVLink: aligned 8-byte stores are single-copy atomic, so every word validates itself and the producer needs no
+ * fence, counter or flag and never waits.  pvb_exchange_wait enqueues a one-CTA kernel that polls this rank's own ring
+ * until every expected word carries `seq` (bounded by timeout_s) and writes the floats to `out` (device fp32
+ * [world][bytes_per_rank/4]; floats_per_rank: HOST array of world counts for ragged shards, NULL = every rank publishes
+ * bytes_per_rank/4 floats).  Ring discipline (caller): before call `seq` is launched, the wait of call `seq - slots/2` must
+ * already be enqueued on the same stream on every rank; seq starts at 1 and increases by 1 per call on every rank alike.
+ * Setup (once): create -> get_handle -> all-gather the 64-byte handles by any means (e.g.
  * torch.distributed.all_gather_object) -> connect.  connect_ptrs takes raw base pointers instead (ranks that live in one
  * process, or memory mapped by other means). */
 typedef struct pvb_exchange pvb_exchange;
@@ -263,7 +264,8 @@ PVB_API int pvb_exchange_connect_ptrs(pvb_exchange *ex, void *const *bases /* wo
 PVB_API int pvb_ransac_voting_v3_push(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
                                       const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
                                       pvb_exchange *exchange, uint64_t seq, pvb_stream_t stream);
-PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, double timeout_s, pvb_stream_t stream);
+PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, const int32_t *floats_per_rank, double timeout_s,
+                              pvb_stream_t stream);
 PVB_API int pvb_exchange_status(pvb_exchange *ex, pvb_stream_t stream); /* synchronises; PVB_ERR_TIMEOUT after a timed-out wait */
 PVB_API int pvb_exchange_destroy(pvb_exchange *ex);
 

@@ -23,7 +23,7 @@ def _make(pvb, world, nmax, K, depth):
 def _gathered(ex, seq, world, nmax, K, sizes):
     from clean_pvnet_b200 import parallel
     buf = torch.empty(world * ex.bytes_per_rank, dtype=torch.uint8, device="cuda:0")
-    ex.wait(seq, buf, timeout_s=5.0)
+    ex.wait(seq, buf, timeout_s=5.0, floats_per_rank=[(hi - lo) * K * 2 for lo, hi in sizes])
     rows = buf.view(world, ex.bytes_per_rank)[:, : nmax * K * 8]
     out = rows.reshape(-1).view(torch.float32).view(world * nmax, K, 2)
     return parallel._unpad(out, sizes, nmax, (K, 2))
@@ -76,7 +76,8 @@ def test_wait_times_out_instead_of_hanging(pvb):
         buf = torch.zeros(2 * exs[0].bytes_per_rank, dtype=torch.uint8, device="cuda:0")
         exs[0].wait(1, buf, timeout_s=0.2)          # rank 1 never ran call 1
         torch.cuda.synchronize()
-        assert torch.isnan(buf.view(torch.float32)).all()
+        got = buf.view(torch.float32).view(2, -1)[:, : K * 2]
+        assert torch.isnan(got).all()
         with pytest.raises(RuntimeError, match="timed out"):
             exs[0].check()
     finally:

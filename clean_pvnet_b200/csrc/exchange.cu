@@ -38,7 +38,8 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
-constexpr int XW_THREADS = 128;
+constexpr int XW_THREADS = 256;
+constexpr int XW_BATCH = 4;          // words per thread loaded back to back before the first is examined
 
 __global__ void __launch_bounds__(XW_THREADS)
 exchange_wait_kernel(const uint2 *__restrict__ recv, unsigned int seq, float *__restrict__ out, int world, int stride_words,
@@ -52,14 +53,25 @@ exchange_wait_kernel(const uint2 *__restrict__ recv, unsigned int seq, float *__
     for (int r = 0; r < world; ++r) {
         const uint2 *src = recv + (size_t)r * stride_words;
         float *dst = out + (size_t)r * stride_words;
-        for (int i = tid; i < counts.n[r]; i += XW_THREADS) {
-            uint2 w = ld_word(src + i);
-            while (w.y != seq) {                             // the word has not arrived yet (it still carries an older seq)
-                if (global_ns() - t0 > timeout_ns) { atomicExch(&s_timed_out, 1); break; }
-                __nanosleep(100);
-                w = ld_word(src + i);
+        const int n = counts.n[r];
+        for (int i0 = tid; i0 < n; i0 += XW_THREADS * XW_BATCH) {
+            uint2 w[XW_BATCH];
+#pragma unroll
+            for (int u = 0; u < XW_BATCH; ++u) {             // independent loads: one L2 round trip for the batch
+                const int i = i0 + u * XW_THREADS;
+                w[u] = (i < n) ? ld_word(src + i) : make_uint2(0u, seq);
             }
-            dst[i] = __uint_as_float(w.x);
+#pragma unroll
+            for (int u = 0; u < XW_BATCH; ++u) {
+                const int i = i0 + u * XW_THREADS;
+                if (i >= n) continue;
+                while (w[u].y != seq) {                      // not arrived yet (the word still carries an older seq)
+                    if (global_ns() - t0 > timeout_ns) { atomicExch(&s_timed_out, 1); break; }
+                    __nanosleep(100);
+                    w[u] = ld_word(src + i);
+                }
+                dst[i] = __uint_as_float(w[u].x);
+            }
         }
     }
     __syncthreads();

@@ -20,10 +20,10 @@ Two ways to make the results visible:
       host logic).  Kept as the portable fallback and as the baseline the fused path is measured against.
 
 Ring discipline of the peer path (what makes reuse of the receive slots safe without acknowledgements): the ring has
-2*depth slots; call s writes slot (s-1) % (2*depth) of every peer; the wait of call s-depth is always enqueued before
-call s is launched (ShardedVotingLayer does it).  A rank that executes call s has therefore finished its wait of call
-s-depth, which needed every peer's call s-depth to be complete, which -- stream order on the peer -- happened after the
-peer's wait of call s-2*depth: the slot call s overwrites has been copied out everywhere.
+2*depth slots; call s writes slot (s-1) % (2*depth) of every peer; a rank starts call s only after its own wait of call
+s-depth has FINISHED (ShardedVotingLayer: an event wait on the compute stream; the wait kernels themselves poll on a side
+stream).  A rank that executes call s has therefore seen every peer's call s-depth complete, and each peer started that
+call only after its own wait of call s-2*depth had finished: the slot call s overwrites has been copied out everywhere.
 """
 import ctypes
 
@@ -146,15 +146,16 @@ class Pending:
     """Result of one sharded call: `.result()` returns the keypoints of the WHOLE batch, [total, K, 2], on this rank's
     device (no host sync); `.local` is this rank's own slice, available at once."""
 
-    def __init__(self, owner, seq, local, sizes, nmax):
-        self._owner, self.seq, self.local, self._sizes, self._nmax = owner, seq, local, sizes, nmax
-        self._gathered = None
-        self._work = None
+    def __init__(self, owner, seq, local):
+        self._owner, self.seq, self.local = owner, seq, local
+        self._gathered = None       # the gathered tensor (peer path: written by the wait kernel on the side stream)
+        self._event = None          # peer path: recorded on the side stream after the wait kernel
+        self._consumed = False      # peer path: the caller's stream has been made to wait for _event
+        self._work = None           # collective path
         self._finish = None
 
     def result(self):
-        if self._gathered is None:
-            self._owner._complete(self)
+        self._owner._complete(self)
         return self._gathered
 
 
@@ -165,9 +166,12 @@ class ShardedVotingLayer:
         p = layer(mask_local, vertex_local, 512, inlier_thresh=0.99, seed=s)   # launches; never blocks on a peer
         kpt = p.result()                                             # [128, 17, 2] on every rank
 
-    Up to `depth` calls may be in flight before a result is asked for; the layer enqueues the wait of call s-depth itself
-    before launching call s (see the module docstring).  `op`/`gather="collective"` let the CPU tests drive the same
-    bookkeeping over gloo with a stand-in operator."""
+    Peer path: every call pushes its results from inside the refit kernel; its wait kernel goes onto a SIDE stream right
+    away (after an event recorded behind the call), so polling for the slowest peer never sits between two steps on the
+    compute stream.  The ring discipline -- call s may start only when this rank's wait of call s-depth has finished -- is
+    an event wait on the compute stream that is already satisfied in the steady state.  `.result()` makes the caller's
+    stream wait for the call's wait kernel.  `op` / `gather="collective"` let the CPU tests drive the same bookkeeping
+    over gloo with a stand-in operator (one all_gather per call, at most `depth` outstanding)."""
 
     def __init__(self, total_images, K, group=None, depth=4, gather="auto", device=None, op=None, timeout_s=10.0):
         self.group = group
@@ -181,8 +185,9 @@ class ShardedVotingLayer:
         self.op = op
         self.timeout_s = timeout_s
         self.seq = 0
-        self.inflight = []          # Pending objects whose wait has not been enqueued yet, oldest first
+        self.inflight = []          # Pending objects not yet completed (collective) / still gating the ring (peer), oldest first
         self.exchange = None
+        self.wait_stream = None
         self.gather_error = None
         if gather not in ("auto", "peer", "collective"):
             raise ValueError("gather must be 'auto', 'peer' or 'collective'")
@@ -211,49 +216,77 @@ class ShardedVotingLayer:
                     self.exchange.close()
                 self.exchange = None
         self.mode = "peer" if self.exchange is not None else "collective"
+        if self.exchange is not None:
+            self.wait_stream = torch.cuda.Stream(device=self.device)
+            self._counts = [(hi - lo) * self.K * 2 for lo, hi in self.sizes]
 
     def __call__(self, mask_local, vertex_local, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000, seed=0, **kw):
         if mask_local.shape[0] != self.hi - self.lo:
             raise ValueError("local batch does not match shard_bounds")
-        # ring discipline: the wait of call seq-depth goes onto the stream before call seq
-        while len(self.inflight) >= self.depth:
-            self._complete(self.inflight[0])
         self.seq += 1
         if self.exchange is not None:
             from .ransac_voting_gpu import ransac_voting_layer_v3
+            cur = torch.cuda.current_stream(self.device)
+            # ring discipline: this rank's wait of call seq-depth must have finished before call seq may overwrite the
+            # peers' slots (module docstring); that wait has been polling on the side stream for `depth` calls already
+            while len(self.inflight) >= self.depth:
+                cur.wait_event(self.inflight.pop(0)._event)
             local = ransac_voting_layer_v3(mask_local, vertex_local, round_hyp_num, inlier_thresh=inlier_thresh,
                                            min_num=min_num, max_num=max_num, seed=seed, img_base=self.lo,
                                            _exchange=(self.exchange.handle, self.seq), **kw)
-            p = Pending(self, self.seq, local, self.sizes, self.nmax)
+            p = Pending(self, self.seq, local)
+            pushed = torch.cuda.Event()
+            pushed.record(cur)
+            with torch.cuda.stream(self.wait_stream):
+                self.wait_stream.wait_event(pushed)
+                buf = torch.empty(self.world * self.exchange.bytes_per_rank, dtype=torch.uint8, device=self.device)
+                self.exchange.wait(p.seq, buf, self.timeout_s, self._counts)
+                p._event = torch.cuda.Event()
+                p._event.record(self.wait_stream)
+            rows = buf.view(self.world, self.exchange.bytes_per_rank)[:, : self.nmax * self.K * 8]
+            out = rows.reshape(self.world * self.nmax * self.K * 8) if rows.is_contiguous() else None
+            p._buf, p._rows = buf, (out, rows)
         else:
+            while len(self.inflight) >= self.depth:
+                self._complete(self.inflight[0])
             op = self.op
             if op is None:
                 from .ransac_voting_gpu import ransac_voting_layer_v3 as op
             local = op(mask_local, vertex_local, round_hyp_num, inlier_thresh=inlier_thresh, min_num=min_num,
                        max_num=max_num, seed=seed, img_base=self.lo, **kw)
-            p = Pending(self, self.seq, local, self.sizes, self.nmax)
+            p = Pending(self, self.seq, local)
             p._finish, p._work = all_gather_ragged(local, self.total, self.group, async_op=True)
         self.inflight.append(p)
         return p
 
     def _complete(self, p):
-        """Enqueue whatever makes p's gathered tensor valid on the current stream (in call order: older calls first)."""
-        while self.inflight and self.inflight[0].seq <= p.seq:
+        """Make p's gathered tensor valid on the current stream."""
+        if self.exchange is not None:
+            if not p._consumed:
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(p._event)
+                p._buf.record_stream(cur)                       # allocated on the side stream, consumed here
+                flat, rows = p._rows
+                if flat is None:                                # bytes_per_rank was padded: compact (a tiny copy kernel)
+                    flat = rows.reshape(self.world * self.nmax * self.K * 8)
+                out = flat.view(torch.float32).view(self.world * self.nmax, self.K, 2)
+                p._gathered = _unpad(out, self.sizes, self.nmax, (self.K, 2))
+                p._consumed = True
+            return
+        while self.inflight and self.inflight[0].seq <= p.seq:   # collectives complete in call order
             q = self.inflight.pop(0)
-            if self.exchange is not None:
-                buf = torch.empty(self.world * self.exchange.bytes_per_rank, dtype=torch.uint8, device=self.device)
-                self.exchange.wait(q.seq, buf, self.timeout_s, [(hi - lo) * self.K * 2 for lo, hi in self.sizes])
-                rows = buf.view(self.world, self.exchange.bytes_per_rank)[:, : self.nmax * self.K * 8]
-                out = rows.reshape(self.world * self.nmax * self.K * 8).view(torch.float32).view(self.world * self.nmax, self.K, 2)
-                q._gathered = _unpad(out, self.sizes, self.nmax, (self.K, 2))
-            else:
-                if q._work is not None:
-                    q._work.wait()
-                q._gathered = q._finish()
+            if q._work is not None:
+                q._work.wait()
+            q._gathered = q._finish()
 
     def drain(self):
-        """Enqueue the waits of everything still in flight (no host sync)."""
-        if self.inflight:
+        """Make everything launched so far complete on the current stream (no host sync)."""
+        if self.exchange is not None:
+            cur = torch.cuda.current_stream(self.device)
+            for q in self.inflight:
+                cur.wait_event(q._event)
+            self.inflight.clear()
+        elif self.inflight:
             self._complete(self.inflight[-1])
 
     def check(self):

@@ -99,3 +99,29 @@ def test_argument_checks(pvb):
             pvb.ransac_voting_layer_v3(mask, vertex, 64, _exchange=(h, 1))
     finally:
         lib.pvb_exchange_destroy(h)
+
+
+def test_sharded_layer_end_to_end_single_rank(pvb):
+    """ShardedVotingLayer's peer path on hardware with a world of one: the push inside the refit kernel, the wait kernels on
+    the side stream, the ring discipline's event waits and .result() -- 11 pipelined calls through a 4-slot ring, every
+    gathered tensor equal to the plain call's result.  (Real peers: bench.py --gpus N, `gather_check`.)"""
+    import socket
+    import torch.distributed as dist
+    from clean_pvnet_b200 import parallel, synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        mask, vertex, _ = synth.make_inputs("small", device="cuda:0", seed=41, B=4)
+        layer = parallel.ShardedVotingLayer(4, vertex.shape[3], depth=2, gather="peer", device="cuda:0")
+        assert layer.mode == "peer"
+        pend = [layer(mask, vertex, 64, inlier_thresh=0.99, max_num=700, seed=900 + i) for i in range(11)]
+        assert len(layer.inflight) <= 2
+        for i in (10, 0, 5, 3):                                   # any order, any number of times
+            want = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, max_num=700, seed=900 + i)
+            assert torch.equal(pend[i].result(), want), i
+            assert torch.equal(pend[i].local, want), i
+            assert pend[i].result() is pend[i].result()
+        layer.check()
+        layer.close()
+    finally:
+        dist.destroy_process_group()

@@ -235,7 +235,31 @@ def run_ours(args):
         layer = parallel.ShardedVotingLayer(total, K, depth=4, gather=args.gather, device=dev)
     pending = []
 
+    # --streams S > 1 (experiment, off by default): consecutive steps go round-robin onto S CUDA streams, so the HBM- and
+    # latency-bound kernels of one step (select, generate, refit) can fill the SMs the other step's ALU-bound vote kernel
+    # leaves idle in its last wave -- the double-buffered way a serving loop would call the layer.  Every step is still a
+    # complete call on a complete batch; ms_per_step is then throughput^-1, not the latency of one call.
+    streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else None
+
     def step(i):
+        if streams is not None:
+            with torch.cuda.stream(streams[i % len(streams)]):
+                return step_on_current_stream(i)
+        return step_on_current_stream(i)
+
+    def join_streams():
+        if streams is not None:
+            cur = torch.cuda.current_stream(dev)
+            for st_ in streams:
+                cur.wait_stream(st_)
+
+    def fork_streams():
+        if streams is not None:
+            cur = torch.cuda.current_stream(dev)
+            for st_ in streams:
+                st_.wait_stream(cur)
+
+    def step_on_current_stream(i):
         if layer is not None:
             # the refit kernel pushes this rank's [B,K,2] into every peer's ring (NVLink stores); the wait of step i-4
             # is enqueued by the layer before step i; everything still pending is waited for inside the timed region (drain)
@@ -259,6 +283,7 @@ def run_ours(args):
     del dbg
     for i in range(max(args.warmup, 3)):
         step(i)
+    join_streams()
     drain()
     torch.cuda.synchronize()
     # NVML polling is free with one process (tools/scale_diag.py at N=1: +1 us/step at 100 Hz) but 8 processes polling at
@@ -273,11 +298,13 @@ def run_ours(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    fork_streams()
     last = None
     t_host0 = time.perf_counter()
     for i in range(args.steps):
         last = step(i)
     t_host1 = time.perf_counter()            # host time to ENQUEUE the steps (the GPU runs behind unless the host is the bottleneck)
+    join_streams()
     gathered = drain()
     ev1.record()
     torch.cuda.synchronize()
@@ -425,6 +452,7 @@ def run_ours(args):
                                    "one torch.distributed all_gather per step, all waited for inside the timed region)"))
                                if world > 1 else "single GPU",
                 "sampling": "philox (in-kernel), new seed every step",
+                "streams": args.streams,
             },
             "clocks": clocks,
             "e2e": {"value": total * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -577,6 +605,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=4, help="images per H2D chunk of the end-to-end path")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="experiment: issue consecutive steps round-robin on this many CUDA streams (default 1)")
     ap.add_argument("--profile-every", type=int, default=4,
                     help="record the stage events (stages_ms, roofline.kernel_ms) on every n-th timed step")
     ap.add_argument("--quick", action="store_true",

@@ -162,3 +162,20 @@ def test_plain_c_consumer_links_and_runs(pvb, tmp_path):
     r = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=60)
     assert r.returncode == 0, r.stdout
     assert "sizeof(pvb_desc)=128" in r.stdout
+
+
+def test_exchange_entry_points_fail_cleanly_without_a_gpu(pvb):
+    """pvb_exchange_*: argument validation runs before any CUDA call, and without a usable device creation returns
+    PVB_ERR_CUDA with a message instead of crashing (there is no CPU implementation of the exchange either)."""
+    lib = pvb._lib.load()
+    h = ctypes.c_void_p()
+    assert lib.pvb_exchange_create(3, 2, 4, 64, ctypes.byref(h)) == pvb._lib.PVB_ERR_INVALID and not h.value
+    assert lib.pvb_exchange_create(0, 17, 4, 64, ctypes.byref(h)) == pvb._lib.PVB_ERR_INVALID        # > PVB_MAX_PEERS
+    assert lib.pvb_exchange_create(0, 2, 1, 64, ctypes.byref(h)) == pvb._lib.PVB_ERR_INVALID         # slots < 2
+    assert lib.pvb_exchange_create(0, 2, 4, 0, ctypes.byref(h)) == pvb._lib.PVB_ERR_INVALID
+    assert b"bytes_per_rank" in lib.pvb_last_error()
+    if not torch.cuda.is_available():
+        rc = lib.pvb_exchange_create(0, 2, 4, 64, ctypes.byref(h))
+        assert rc == pvb._lib.PVB_ERR_CUDA and not h.value and lib.pvb_last_error()
+    assert lib.pvb_exchange_wait(None, 1, None, None, 1.0, None) == pvb._lib.PVB_ERR_INVALID
+    assert lib.pvb_exchange_destroy(None) == pvb._lib.PVB_OK

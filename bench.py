@@ -46,8 +46,10 @@ def workload_string(name, cfg, layout, per_gpu_images):
     return (f"{name}: B={per_gpu_images} images per GPU per step, {cfg['H']}x{cfg['W']}, K={cfg['K']}, hn={HN}, "
             f"inlier_thresh={THRESH}, fill~30%, int64 mask, vertex layout={layout}, max_num=30000")
 # dram__bytes_read.sum + dram__bytes_write.sum of one vote_kernel launch on this workload, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_summary.txt): 39 394 304 + 256 bytes
-VOTE_KERNEL_DRAM_BYTES = 39394560
+# `ncu --set full` capture (profiles/r02_ncu_select_vote_refit.txt; ncu flushes the caches before the launch): 39 422 976 + 0.
+# In a real step the compacted arrays are still in L2: 4.40 MB + 1.79 MB (profiles/r02_traffic_warm.csv, --cache-control none)
+VOTE_KERNEL_DRAM_BYTES = 39422976
+VOTE_KERNEL_DRAM_BYTES_WARM = 6190000
 
 
 def _env_int(name, default):
@@ -500,8 +502,10 @@ def run_ours(args):
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None,
                 "traffic": args.traffic if args.traffic is not None else (VOTE_KERNEL_DRAM_BYTES if wl == "cfg2" else None),
-                "traffic_source": "constant from the committed `ncu --set full` capture of this kernel on this workload "
-                                  "(profiles/r01_ncu_summary.txt); not re-measured per run",
+                "traffic_warm_caches": VOTE_KERNEL_DRAM_BYTES_WARM if wl == "cfg2" else None,
+                "traffic_source": "constants from the committed ncu captures of this kernel on this workload: `--set full` with "
+                                  "ncu's cache flush (profiles/r02_ncu_select_vote_refit.txt) and `--cache-control none` "
+                                  "(profiles/r02_traffic_warm.csv); not re-measured per run",
                 "kernel": "pvb::vote_kernel<4,128,8,512,4>",
                 "kernel_ms": vote_ms, "algorithmic_bytes": bytes_alg,
                 "peak_source": peak_src,

@@ -73,6 +73,7 @@ SIGNATURES = {
     "pvb_exchange_connect": (ctypes.c_int, [_vp, _vp]),
     "pvb_exchange_connect_ptrs": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_void_p)]),
     "pvb_ransac_voting_v3_push": (ctypes.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, ctypes.c_uint64, _vp]),
+    "pvb_estimate_voting_distribution_push": (ctypes.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, ctypes.c_uint64, _vp]),
     "pvb_exchange_wait": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _vp, ctypes.c_double, _vp]),
     "pvb_exchange_status": (ctypes.c_int, [_vp, _vp]),
     "pvb_exchange_destroy": (ctypes.c_int, [_vp]),

@@ -326,24 +326,47 @@ PVB_API int pvb_decode_v3(const pvb_desc *d, const float *seg, int32_t classes, 
                   nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
-PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
-                                     const int32_t *idxs, const float *selection, float *out_cov, void *workspace,
-                                     size_t workspace_bytes, pvb_stream_t stream)
+static int run_distribution(const pvb_desc *d, const void *mask, const float *vertex, const float *mean, const int32_t *idxs,
+                            const float *selection, float *out_cov, void *workspace, size_t workspace_bytes, pvb_exchange *ex,
+                            uint64_t seq, cudaStream_t st)
 {
     Plan P;
     int rc = make_plan(d, mask, vertex, idxs, selection, workspace, workspace_bytes, 3u, 4u, &P);
     if (rc) return rc;
     if (!mean || !out_cov) return fail(PVB_ERR_INVALID, "mean/out_cov is NULL");
-    if (d->B == 0) return PVB_OK;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PeerPush pp;
+    rc = exchange_push_args(ex, seq, (size_t)d->B * d->K * 4 * sizeof(float), &pp);
+    if (rc) return rc;
+    if (d->B == 0) {
+        if (pp.world > 0) return fail(PVB_ERR_INVALID, "an exchanging call needs B >= 1 on every rank");
+        return PVB_OK;
+    }
     ProfCall *pc = prof_begin(true);
     rc = run_front(P, st, pc);
     if (rc) return rc;
     prof_start(pc, PVB_STAGE_FINISH, st);
-    cudaError_t e = launch_covariance(P.v, mean, out_cov, st);
+    cudaError_t e = launch_covariance(P.v, mean, out_cov, pp, st);
     if (e != cudaSuccess) return cuda_fail(e, "covariance kernel");
     prof_end(pc, PVB_STAGE_FINISH, st);
     return PVB_OK;
+}
+
+PVB_API int pvb_estimate_voting_distribution(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
+                                     const int32_t *idxs, const float *selection, float *out_cov, void *workspace,
+                                     size_t workspace_bytes, pvb_stream_t stream)
+{
+    return run_distribution(d, mask, vertex, mean, idxs, selection, out_cov, workspace, workspace_bytes, nullptr, 0,
+                            static_cast<cudaStream_t>(stream));
+}
+
+PVB_API int pvb_estimate_voting_distribution_push(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
+                                                  const int32_t *idxs, const float *selection, float *out_cov, void *workspace,
+                                                  size_t workspace_bytes, pvb_exchange *exchange, uint64_t seq,
+                                                  pvb_stream_t stream)
+{
+    if (!exchange) return fail(PVB_ERR_INVALID, "exchange is NULL");
+    return run_distribution(d, mask, vertex, mean, idxs, selection, out_cov, workspace, workspace_bytes, exchange, seq,
+                            static_cast<cudaStream_t>(stream));
 }
 
 PVB_API int pvb_uncertainty_weights(const float *cov, float *weights, int32_t n, pvb_stream_t stream)

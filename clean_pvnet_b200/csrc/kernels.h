@@ -72,8 +72,8 @@ cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs,
 struct ExchangeCounts { int n[PVB_MAX_PEERS]; };
 cudaError_t launch_exchange_wait(const uint2 *recv, unsigned int seq, float *out, int world, int stride_words,
                                  const ExchangeCounts &counts, unsigned long long timeout_ns, int *status, cudaStream_t st);
-// ratio/threshold/weighted covariance -> out_cov [B][K][2][2]
-cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, cudaStream_t st);
+// ratio/threshold/weighted covariance -> out_cov [B][K][2][2] (+ the same exchange tail as the refit kernel, 4 floats per unit)
+cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, const PeerPush &pp, cudaStream_t st);
 
 // inv(sqrtm(cov)) packed (wxx,wxy,wyy): cov [n][2][2] -> w [n][3]
 cudaError_t launch_pnp_weights(const float *cov, float *w, int n, cudaStream_t st);

@@ -326,6 +326,19 @@ cudaError_t launch_vote(const VoteArgs &a, bool zero_counts, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// Multi-GPU exchange tail shared by the refit and the covariance kernel: one thread stores NV floats of unit `bk` into every
+// peer's receive slot (r == own rank: local) as self-validating 8-byte words {float bits, seq} (kernels.h, PeerPush).
+template <int NV>
+__device__ __forceinline__ void peer_push(const PeerPush &pp, size_t bk, const float (&v)[NV])
+{
+    for (int r = 0; r < pp.world; ++r) {
+        uint2 *dst = pp.recv[r] + bk * NV;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + i), "r"(__float_as_uint(v[i])), "r"(pp.seq) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // winner (torch.max semantics: first maximal index, ransac_voting_gpu.py:160-167) + least-squares
 // refit over the winner's inliers (:177-196).  RF_CHUNK pixels per CTA, ticketed deterministic reduction.
@@ -447,12 +460,8 @@ refit_kernel(VoteArgs a, float2 *__restrict__ win, RefitScratch rs, float *__res
     // receive slot over NVLink (r == own rank: local) as two self-validating 8-byte words {float bits, seq}.  Fire and
     // forget: no fence, no counter, no flag (kernels.h, PeerPush).
     if (pp.world <= 0 || tid != 0) return;
-    const uint2 wx = make_uint2(__float_as_uint(res.x), pp.seq), wy = make_uint2(__float_as_uint(res.y), pp.seq);
-    for (int r = 0; r < pp.world; ++r) {
-        uint2 *dst = pp.recv[r] + bk * 2;
-        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(wx.x), "r"(wx.y) : "memory");
-        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 1), "r"(wy.x), "r"(wy.y) : "memory");
-    }
+    const float v[2] = {res.x, res.y};
+    peer_push<2>(pp, bk, v);
 }
 
 cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs, float *out_kpt, const PeerPush &pp,
@@ -469,7 +478,7 @@ cudaError_t launch_refit(const VoteArgs &a, float2 *win, const RefitScratch &rs,
 constexpr int CV_THREADS = 256;
 
 __global__ void __launch_bounds__(CV_THREADS)
-covariance_kernel(VoteArgs a, const float *__restrict__ mean, float *__restrict__ cov)
+covariance_kernel(VoteArgs a, const float *__restrict__ mean, float *__restrict__ cov, PeerPush pp)
 {
     const int k = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -514,15 +523,16 @@ covariance_kernel(VoteArgs a, const float *__restrict__ mean, float *__restrict_
             for (int i = 0; i < 4; ++i) s[i] += s_acc[w][i];
         const double den = (double)__fadd_rn((float)s[3], 1e-3f);
         float *c = cov + bk * 4;
-        c[0] = (float)(s[0] / den); c[1] = (float)(s[1] / den);
-        c[2] = (float)(s[1] / den); c[3] = (float)(s[2] / den);
+        const float v[4] = {(float)(s[0] / den), (float)(s[1] / den), (float)(s[1] / den), (float)(s[2] / den)};
+        c[0] = v[0]; c[1] = v[1]; c[2] = v[2]; c[3] = v[3];
+        if (pp.world > 0) peer_push<4>(pp, bk, v);          // multi-GPU: the 2x2 covariance goes to every peer as it is produced
     }
 }
 
-cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, cudaStream_t st)
+cudaError_t launch_covariance(const VoteArgs &a, const float *mean, float *out_cov, const PeerPush &pp, cudaStream_t st)
 {
     dim3 g(a.K, a.B);
-    covariance_kernel<<<g, CV_THREADS, 0, st>>>(a, mean, out_cov);
+    covariance_kernel<<<g, CV_THREADS, 0, st>>>(a, mean, out_cov, pp);
     return cudaGetLastError();
 }
 

@@ -143,11 +143,11 @@ class PeerExchange:
 
 
 class Pending:
-    """Result of one sharded call: `.result()` returns the keypoints of the WHOLE batch, [total, K, 2], on this rank's
-    device (no host sync); `.local` is this rank's own slice, available at once."""
+    """Result of one sharded call: `.result()` returns the result of the WHOLE batch ([total, K, 2] keypoints or
+    [total, K, 2, 2] covariances) on this rank's device (no host sync); `.local` is this rank's own slice, available at once."""
 
-    def __init__(self, owner, seq, local):
-        self._owner, self.seq, self.local = owner, seq, local
+    def __init__(self, channel, seq, local):
+        self._channel, self.seq, self.local = channel, seq, local
         self._gathered = None       # the gathered tensor (peer path: written by the wait kernel on the side stream)
         self._event = None          # peer path: recorded on the side stream after the wait kernel
         self._consumed = False      # peer path: the caller's stream has been made to wait for _event
@@ -155,25 +155,128 @@ class Pending:
         self._finish = None
 
     def result(self):
-        self._owner._complete(self)
+        self._channel.complete(self)
         return self._gathered
 
 
+class _Channel:
+    """One stream of sharded calls whose per-rank results have the shape [n_r, K, *unit]: its own receive ring (peer path),
+    sequence numbers, in-flight list and side stream.  The keypoints and the covariances of a ShardedVotingLayer are two
+    channels."""
+
+    def __init__(self, owner, unit, use_peer, gather):
+        self.o = owner
+        self.unit = tuple(unit)                     # (2,) keypoints, (2, 2) covariances
+        self.nf = 1
+        for u in self.unit:
+            self.nf *= u                            # floats per (image, keypoint)
+        self.seq = 0
+        self.inflight = []                          # oldest first
+        self.exchange = None
+        self.wait_stream = None
+        self.error = None
+        o = owner
+        if use_peer:
+            ok = 1
+            try:
+                self.exchange = PeerExchange(o.nmax * o.K * self.nf * 4, 2 * o.depth, group=o.group, device=o.device)
+                self.exchange.connect_ipc()
+            except Exception as e:          # no P2P between the GPUs, IPC unavailable, ...
+                self.error = str(e)
+                ok = 0
+            # all ranks must agree on the path
+            flag = torch.tensor([ok], dtype=torch.int32, device=o.device if dist.get_backend(o.group) == "nccl" else "cpu")
+            if o.world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=o.group)
+            if int(flag.item()) == 0:
+                if gather == "peer":
+                    raise RuntimeError(f"peer exchange unavailable: {self.error or 'failed on another rank'}")
+                if self.exchange is not None:
+                    self.exchange.close()
+                self.exchange = None
+        if self.exchange is not None:
+            self.wait_stream = torch.cuda.Stream(device=o.device)
+            self.counts = [(hi - lo) * o.K * self.nf for lo, hi in o.sizes]
+            self.row_bytes = o.nmax * o.K * self.nf * 4
+
+    def launch(self, run_local):
+        """run_local(exchange_arg) -> this rank's result tensor; exchange_arg is (handle, seq) on the peer path, else None."""
+        o = self.o
+        self.seq += 1
+        if self.exchange is not None:
+            cur = torch.cuda.current_stream(o.device)
+            # ring discipline: this rank's wait of call seq-depth must have finished before call seq may overwrite the
+            # peers' slots (module docstring); that wait has been polling on the side stream for `depth` calls already
+            while len(self.inflight) >= o.depth:
+                cur.wait_event(self.inflight.pop(0)._event)
+            local = run_local((self.exchange.handle, self.seq))
+            p = Pending(self, self.seq, local)
+            pushed = torch.cuda.Event()
+            pushed.record(cur)
+            with torch.cuda.stream(self.wait_stream):
+                self.wait_stream.wait_event(pushed)
+                buf = torch.empty(o.world * self.exchange.bytes_per_rank, dtype=torch.uint8, device=o.device)
+                self.exchange.wait(p.seq, buf, o.timeout_s, self.counts)
+                p._event = torch.cuda.Event()
+                p._event.record(self.wait_stream)
+            p._buf = buf
+        else:
+            while len(self.inflight) >= o.depth:
+                self.complete(self.inflight[0])
+            local = run_local(None)
+            p = Pending(self, self.seq, local)
+            p._finish, p._work = all_gather_ragged(local, o.total, o.group, async_op=True)
+        self.inflight.append(p)
+        return p
+
+    def complete(self, p):
+        """Make p's gathered tensor valid on the current stream."""
+        o = self.o
+        if self.exchange is not None:
+            if not p._consumed:
+                cur = torch.cuda.current_stream(o.device)
+                cur.wait_event(p._event)
+                p._buf.record_stream(cur)                       # allocated on the side stream, consumed here
+                rows = p._buf.view(o.world, self.exchange.bytes_per_rank)[:, : self.row_bytes]
+                flat = rows.reshape(o.world * self.row_bytes)   # a view unless bytes_per_rank was padded to 16
+                out = flat.view(torch.float32).view(o.world * o.nmax, o.K, *self.unit)
+                p._gathered = _unpad(out, o.sizes, o.nmax, (o.K,) + self.unit)
+                p._consumed = True
+            return
+        while self.inflight and self.inflight[0].seq <= p.seq:   # collectives complete in call order
+            q = self.inflight.pop(0)
+            if q._work is not None:
+                q._work.wait()
+            q._gathered = q._finish()
+
+    def drain(self):
+        if self.exchange is not None:
+            cur = torch.cuda.current_stream(self.o.device)
+            for q in self.inflight:
+                cur.wait_event(q._event)
+            self.inflight.clear()
+        elif self.inflight:
+            self.complete(self.inflight[-1])
+
+
 class ShardedVotingLayer:
-    """ransac_voting_layer_v3 over a batch sharded across the ranks of `group`.
+    """ransac_voting_layer_v3 (and estimate_voting_distribution_with_mean) over a batch sharded across the ranks of `group`.
 
         layer = ShardedVotingLayer(total_images=128, K=17)           # collective (peer rings are mapped here)
         p = layer(mask_local, vertex_local, 512, inlier_thresh=0.99, seed=s)   # launches; never blocks on a peer
         kpt = p.result()                                             # [128, 17, 2] on every rank
+        c = layer.distribution(mask_local, vertex_local, p.local, seed=s)      # the other half of resnet18.py:71-72
+        var = c.result()                                             # [128, 17, 2, 2] on every rank
 
-    Peer path: every call pushes its results from inside the refit kernel; its wait kernel goes onto a SIDE stream right
-    away (after an event recorded behind the call), so polling for the slowest peer never sits between two steps on the
-    compute stream.  The ring discipline -- call s may start only when this rank's wait of call s-depth has finished -- is
-    an event wait on the compute stream that is already satisfied in the steady state.  `.result()` makes the caller's
-    stream wait for the call's wait kernel.  `op` / `gather="collective"` let the CPU tests drive the same bookkeeping
-    over gloo with a stand-in operator (one all_gather per call, at most `depth` outstanding)."""
+    Peer path: every call pushes its results from inside the producing kernel (refit / covariance); its wait kernel goes
+    onto a SIDE stream right away (after an event recorded behind the call), so polling for the slowest peer never sits
+    between two steps on the compute stream.  The ring discipline -- call s may start only when this rank's wait of call
+    s-depth has finished -- is an event wait on the compute stream that is already satisfied in the steady state.
+    `.result()` makes the caller's stream wait for the call's wait kernel.  `op` / `gather="collective"` let the CPU tests
+    drive the same bookkeeping over gloo with a stand-in operator (one all_gather per call, at most `depth` outstanding)."""
 
-    def __init__(self, total_images, K, group=None, depth=4, gather="auto", device=None, op=None, timeout_s=10.0):
+    def __init__(self, total_images, K, group=None, depth=4, gather="auto", device=None, op=None, timeout_s=10.0,
+                 with_distribution=True):
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.total, self.K, self.depth = int(total_images), int(K), int(depth)
@@ -184,11 +287,6 @@ class ShardedVotingLayer:
         self.lo, self.hi = self.sizes[self.rank]
         self.op = op
         self.timeout_s = timeout_s
-        self.seq = 0
-        self.inflight = []          # Pending objects not yet completed (collective) / still gating the ring (peer), oldest first
-        self.exchange = None
-        self.wait_stream = None
-        self.gather_error = None
         if gather not in ("auto", "peer", "collective"):
             raise ValueError("gather must be 'auto', 'peer' or 'collective'")
         use_peer = gather == "peer" or (gather == "auto" and op is None and torch.cuda.is_available())
@@ -196,109 +294,70 @@ class ShardedVotingLayer:
             if gather == "peer":
                 raise ValueError("gather='peer' needs at least one image on every rank")
             use_peer = False
-        if use_peer:
+        self.device = None
+        if use_peer or (op is None and torch.cuda.is_available()):
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-            ok = 1
-            try:
-                self.exchange = PeerExchange(self.nmax * self.K * 2 * 4, 2 * self.depth, group=group, device=self.device)
-                self.exchange.connect_ipc()
-            except Exception as e:          # no P2P between the GPUs, IPC unavailable, ...
-                self.gather_error = str(e)
-                ok = 0
-            # all ranks must agree on the path
-            flag = torch.tensor([ok], dtype=torch.int32, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
-            if self.world > 1:
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) == 0:
-                if gather == "peer":
-                    raise RuntimeError(f"peer exchange unavailable: {self.gather_error or 'failed on another rank'}")
-                if self.exchange is not None:
-                    self.exchange.close()
-                self.exchange = None
-        self.mode = "peer" if self.exchange is not None else "collective"
-        if self.exchange is not None:
-            self.wait_stream = torch.cuda.Stream(device=self.device)
-            self._counts = [(hi - lo) * self.K * 2 for lo, hi in self.sizes]
+        self._kpt = _Channel(self, (2,), use_peer, gather)
+        self._cov = _Channel(self, (2, 2), use_peer and self._kpt.exchange is not None, gather) if with_distribution else None
+        self.mode = "peer" if self._kpt.exchange is not None else "collective"
+        self.gather_error = self._kpt.error
+
+    # the keypoint channel's bookkeeping, exposed for tests and tools
+    @property
+    def inflight(self):
+        return self._kpt.inflight
+
+    @property
+    def exchange(self):
+        return self._kpt.exchange
 
     def __call__(self, mask_local, vertex_local, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000, seed=0, **kw):
         if mask_local.shape[0] != self.hi - self.lo:
             raise ValueError("local batch does not match shard_bounds")
-        self.seq += 1
-        if self.exchange is not None:
-            from .ransac_voting_gpu import ransac_voting_layer_v3
-            cur = torch.cuda.current_stream(self.device)
-            # ring discipline: this rank's wait of call seq-depth must have finished before call seq may overwrite the
-            # peers' slots (module docstring); that wait has been polling on the side stream for `depth` calls already
-            while len(self.inflight) >= self.depth:
-                cur.wait_event(self.inflight.pop(0)._event)
-            local = ransac_voting_layer_v3(mask_local, vertex_local, round_hyp_num, inlier_thresh=inlier_thresh,
-                                           min_num=min_num, max_num=max_num, seed=seed, img_base=self.lo,
-                                           _exchange=(self.exchange.handle, self.seq), **kw)
-            p = Pending(self, self.seq, local)
-            pushed = torch.cuda.Event()
-            pushed.record(cur)
-            with torch.cuda.stream(self.wait_stream):
-                self.wait_stream.wait_event(pushed)
-                buf = torch.empty(self.world * self.exchange.bytes_per_rank, dtype=torch.uint8, device=self.device)
-                self.exchange.wait(p.seq, buf, self.timeout_s, self._counts)
-                p._event = torch.cuda.Event()
-                p._event.record(self.wait_stream)
-            rows = buf.view(self.world, self.exchange.bytes_per_rank)[:, : self.nmax * self.K * 8]
-            out = rows.reshape(self.world * self.nmax * self.K * 8) if rows.is_contiguous() else None
-            p._buf, p._rows = buf, (out, rows)
-        else:
-            while len(self.inflight) >= self.depth:
-                self._complete(self.inflight[0])
-            op = self.op
-            if op is None:
-                from .ransac_voting_gpu import ransac_voting_layer_v3 as op
-            local = op(mask_local, vertex_local, round_hyp_num, inlier_thresh=inlier_thresh, min_num=min_num,
-                       max_num=max_num, seed=seed, img_base=self.lo, **kw)
-            p = Pending(self, self.seq, local)
-            p._finish, p._work = all_gather_ragged(local, self.total, self.group, async_op=True)
-        self.inflight.append(p)
-        return p
+        op = self.op
+        if op is None:
+            from .ransac_voting_gpu import ransac_voting_layer_v3 as op
 
-    def _complete(self, p):
-        """Make p's gathered tensor valid on the current stream."""
-        if self.exchange is not None:
-            if not p._consumed:
-                cur = torch.cuda.current_stream(self.device)
-                cur.wait_event(p._event)
-                p._buf.record_stream(cur)                       # allocated on the side stream, consumed here
-                flat, rows = p._rows
-                if flat is None:                                # bytes_per_rank was padded: compact (a tiny copy kernel)
-                    flat = rows.reshape(self.world * self.nmax * self.K * 8)
-                out = flat.view(torch.float32).view(self.world * self.nmax, self.K, 2)
-                p._gathered = _unpad(out, self.sizes, self.nmax, (self.K, 2))
-                p._consumed = True
-            return
-        while self.inflight and self.inflight[0].seq <= p.seq:   # collectives complete in call order
-            q = self.inflight.pop(0)
-            if q._work is not None:
-                q._work.wait()
-            q._gathered = q._finish()
+        def run(ex):
+            extra = dict(kw, _exchange=ex) if ex is not None else kw
+            return op(mask_local, vertex_local, round_hyp_num, inlier_thresh=inlier_thresh, min_num=min_num,
+                      max_num=max_num, seed=seed, img_base=self.lo, **extra)
+        return self._kpt.launch(run)
+
+    def distribution(self, mask_local, vertex_local, mean_local, round_hyp_num=256, min_hyp_num=4096, inlier_thresh=0.99,
+                     min_num=5, max_num=30000, seed=0, op=None, **kw):
+        """estimate_voting_distribution_with_mean on this rank's images; `.result()` is the covariance of the whole batch."""
+        if self._cov is None:
+            raise RuntimeError("constructed with with_distribution=False")
+        if mask_local.shape[0] != self.hi - self.lo:
+            raise ValueError("local batch does not match shard_bounds")
+        if op is None:
+            from .ransac_voting_gpu import estimate_voting_distribution_with_mean as op
+
+        def run(ex):
+            extra = dict(kw, _exchange=ex) if ex is not None else kw
+            return op(mask_local, vertex_local, mean_local, round_hyp_num=round_hyp_num, min_hyp_num=min_hyp_num,
+                      inlier_thresh=inlier_thresh, min_num=min_num, max_num=max_num, seed=seed, img_base=self.lo, **extra)[1]
+        return self._cov.launch(run)
 
     def drain(self):
         """Make everything launched so far complete on the current stream (no host sync)."""
-        if self.exchange is not None:
-            cur = torch.cuda.current_stream(self.device)
-            for q in self.inflight:
-                cur.wait_event(q._event)
-            self.inflight.clear()
-        elif self.inflight:
-            self._complete(self.inflight[-1])
+        self._kpt.drain()
+        if self._cov is not None:
+            self._cov.drain()
 
     def check(self):
         """Host sync + error check of the peer path (a timed-out wait fills its result with NaN and raises here)."""
         self.drain()
-        if self.exchange is not None:
-            self.exchange.check()
+        for ch in (self._kpt, self._cov):
+            if ch is not None and ch.exchange is not None:
+                ch.exchange.check()
 
     def close(self):
-        if self.exchange is not None:
-            self.exchange.close()
-            self.exchange = None
+        for ch in (self._kpt, self._cov):
+            if ch is not None and ch.exchange is not None:
+                ch.exchange.close()
+                ch.exchange = None
 
 
 def sharded_ransac_voting_layer_v3(mask_local, vertex_local, round_hyp_num, total_images, inlier_thresh=0.999,

@@ -227,7 +227,11 @@ def _run(op, mask, vertex, hn, inlier_thresh, min_num, max_num, mean=None, idxs=
                 raise RuntimeError("mean must be a CUDA tensor [b,vn,2]")
             mean_c = mean.float().contiguous()
             out = torch.empty((B, K, 2, 2), dtype=torch.float32, device=dev)
-            if B:
+            if exchange is not None:
+                _lib.check(lib.pvb_estimate_voting_distribution_push(d, mask.data_ptr(), vertex.data_ptr(), mean_c.data_ptr(),
+                                                                     ip, sp, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                                     exchange[0], exchange[1], stream))
+            elif B:
                 _lib.check(lib.pvb_estimate_voting_distribution(d, mask.data_ptr(), vertex.data_ptr(),
                                                                 mean_c.data_ptr(), ip, sp, out.data_ptr(),
                                                                 ws.data_ptr(), ws.numel(), stream))
@@ -274,7 +278,7 @@ def ransac_voting_layer(mask, vertex, round_hyp_num, inlier_thresh=0.999, confid
 def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128,
                                            inlier_thresh=0.99, min_num=5, max_num=30000, output_hyp=False, *,
                                            idxs=None, selection=None, rng="philox", seed=None, img_base=0,
-                                           capacity=None, debug=False):
+                                           capacity=None, debug=False, _exchange=None):
     """Drop-in for ransac_voting_gpu.py:202-274: returns (mean, cov[b,vn,2,2]).
     `topk` and `output_hyp` are unused by the reference as well."""
     del topk, output_hyp
@@ -282,7 +286,7 @@ def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256
     hn = int(round_hyp_num) * rounds
     res = _run("dist", mask, vertex, hn, inlier_thresh, min_num, max_num, mean=mean, idxs=idxs,
                selection=selection, rng=rng, seed=seed, img_base=img_base, capacity=capacity, debug=debug,
-               rounds=rounds, round_hn=int(round_hyp_num))
+               rounds=rounds, round_hn=int(round_hyp_num), exchange=_exchange)
     if debug:
         return mean, res[0], res[1]
     return mean, res

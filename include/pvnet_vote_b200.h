@@ -264,6 +264,12 @@ PVB_API int pvb_exchange_connect_ptrs(pvb_exchange *ex, void *const *bases /* wo
 PVB_API int pvb_ransac_voting_v3_push(const pvb_desc *d, const void *mask, const float *vertex, const int32_t *idxs,
                                       const float *selection, float *out_kpt, void *workspace, size_t workspace_bytes,
                                       pvb_exchange *exchange, uint64_t seq, pvb_stream_t stream);
+/* the same for the second half of the un_pnp pair (resnet18.py:71-72): every [2,2] covariance goes to every peer as the
+ * covariance kernel produces it (4 floats per (image, keypoint); use an exchange of its own: bytes_per_rank >= B*K*16) */
+PVB_API int pvb_estimate_voting_distribution_push(const pvb_desc *d, const void *mask, const float *vertex, const float *mean,
+                                                  const int32_t *idxs, const float *selection, float *out_cov, void *workspace,
+                                                  size_t workspace_bytes, pvb_exchange *exchange, uint64_t seq,
+                                                  pvb_stream_t stream);
 PVB_API int pvb_exchange_wait(pvb_exchange *ex, uint64_t seq, void *out, const int32_t *floats_per_rank, double timeout_s,
                               pvb_stream_t stream);
 PVB_API int pvb_exchange_status(pvb_exchange *ex, pvb_stream_t stream); /* synchronises; PVB_ERR_TIMEOUT after a timed-out wait */

@@ -29,6 +29,15 @@ def _oracle_op(mask, vertex, hn, inlier_thresh=0.999, min_num=5, max_num=30000, 
     return torch.from_numpy(out)
 
 
+def _oracle_dist_op(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, inlier_thresh=0.99, min_num=5, max_num=30000,
+                    seed=0, img_base=0):
+    import pvnet_oracle
+    _, cov = pvnet_oracle.estimate_voting_distribution_with_mean(mask.numpy(), vertex.numpy(), mean.numpy(), round_hyp_num=round_hyp_num,
+                                                                  min_hyp_num=min_hyp_num, inlier_thresh=inlier_thresh, min_num=min_num,
+                                                                  max_num=max_num, seed=seed, img_base=img_base)
+    return mean, torch.from_numpy(cov)
+
+
 def _worker(rank, world, port, total, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -65,11 +74,16 @@ def _layer_worker(rank, world, port, total, steps, depth, q):
         outs = [None] * steps
         for s in reversed(range(steps)):                       # out of order on purpose
             outs[s] = pend[s].result().numpy()
+        # the other half of the un_pnp pair on its own channel: covariances of the whole batch on every rank
+        cov = layer.distribution(mask[lo:hi], vertex[lo:hi], pend[0].local, round_hyp_num=16, min_hyp_num=64, max_num=300, seed=7,
+                                 op=_oracle_dist_op)
+        covs = cov.result().numpy()
         layer.check()
         assert not layer.inflight
         assert np.array_equal(pend[0].local.numpy(), outs[0][lo:hi])
+        assert np.array_equal(cov.local.numpy(), covs[lo:hi]) and covs.shape == (total, vertex.shape[3], 2, 2)
         if rank == 0:
-            q.put(np.stack(outs))
+            q.put((np.stack(outs), covs))
     finally:
         dist.destroy_process_group()
 
@@ -84,7 +98,7 @@ def test_sharded_layer_pipelined_calls(total, depth):
     procs = [ctx.Process(target=_layer_worker, args=(r, 2, port, total, steps, depth, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=240)
+    got, covs = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -93,6 +107,8 @@ def test_sharded_layer_pipelined_calls(total, depth):
     for s in range(steps):
         want = _oracle_op(mask, vertex, 16, inlier_thresh=0.99, max_num=300, seed=100 + s).numpy()
         assert np.array_equal(got[s], want), s
+    _, want_cov = _oracle_dist_op(mask, vertex, torch.from_numpy(got[0]), round_hyp_num=16, min_hyp_num=64, max_num=300, seed=7)
+    assert np.array_equal(covs, want_cov.numpy())
 
 
 def test_shard_bounds():

@@ -65,6 +65,35 @@ def test_pushed_results_equal_the_single_gpu_result(pvb, world, total):
             e.close()
 
 
+def test_pushed_covariances_equal_the_single_gpu_result(pvb):
+    """pvb_estimate_voting_distribution_push: 3 "ranks", ragged shards, 4 floats per (image, keypoint)."""
+    from clean_pvnet_b200 import parallel, synth
+    world, total = 3, 5
+    mask, vertex, _ = synth.make_inputs("small", device="cuda:0", seed=35, B=total)
+    K = vertex.shape[3]
+    sizes = [parallel.shard_bounds(total, world, r) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in sizes)
+    mean = pvb.ransac_voting_layer_v3(mask, vertex, 64, inlier_thresh=0.99, seed=1, max_num=700)
+    _, want = pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=64, min_hyp_num=256, max_num=700, seed=9)
+    exs = [parallel.PeerExchange(nmax * K * 16, 4, rank=r, world=world, device="cuda:0") for r in range(world)]
+    try:
+        for e in exs:
+            e.connect_local(exs)
+        for r, (lo, hi) in enumerate(sizes):
+            pvb.estimate_voting_distribution_with_mean(mask[lo:hi], vertex[lo:hi], mean[lo:hi], round_hyp_num=64, min_hyp_num=256,
+                                                       max_num=700, seed=9, img_base=lo, _exchange=(exs[r].handle, 1))
+        for r in range(world):
+            buf = torch.empty(world * exs[r].bytes_per_rank, dtype=torch.uint8, device="cuda:0")
+            exs[r].wait(1, buf, timeout_s=5.0, floats_per_rank=[(hi - lo) * K * 4 for lo, hi in sizes])
+            rows = buf.view(world, exs[r].bytes_per_rank)[:, : nmax * K * 16]
+            got = parallel._unpad(rows.reshape(-1).view(torch.float32).view(world * nmax, K, 2, 2), sizes, nmax, (K, 2, 2))
+            assert torch.equal(got, want), r
+            exs[r].check()
+    finally:
+        for e in exs:
+            e.close()
+
+
 def test_wait_times_out_instead_of_hanging(pvb):
     """A rank that never publishes: the wait kernel gives up after timeout_s, poisons its output and the status call raises."""
     from clean_pvnet_b200 import synth
@@ -121,6 +150,12 @@ def test_sharded_layer_end_to_end_single_rank(pvb):
             assert torch.equal(pend[i].result(), want), i
             assert torch.equal(pend[i].local, want), i
             assert pend[i].result() is pend[i].result()
+        # the covariance channel: pushed from the covariance kernel, gathered the same way
+        mean = pend[3].local
+        c = layer.distribution(mask, vertex, mean, round_hyp_num=64, min_hyp_num=256, max_num=700, seed=77)
+        _, want_cov = pvb.estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=64, min_hyp_num=256, max_num=700,
+                                                                 seed=77)
+        assert torch.equal(c.result(), want_cov) and torch.equal(c.local, want_cov)
         layer.check()
         layer.close()
     finally:

@@ -292,10 +292,16 @@ def run_ours(args):
     # 100 Hz cost every rank 31 us per 0.65 ms step (profiles/r02_scale_diag_n8.txt): rank 0 samples its GPU, the others do not
     sampler = ClockSampler(local) if rank == 0 else None
     lib.pvb_profile_reset()
-    lib.pvb_profile_enable(args.profile_every)     # stage events on every n-th step only: each record drains the pipeline
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if layer is not None:
+        # GPU-side alignment of the ranks' timelines (untimed): one more step whose gathered result is waited for on the
+        # compute stream -- its wait kernel ends when the LAST rank's results have arrived, i.e. at the same moment (+- an
+        # NVLink hop) on every rank, so ev0 below is recorded simultaneously everywhere.  The host-side barrier above lets
+        # ranks leave up to a few hundred microseconds apart, which a 20-step region would pay as 10-20 us per step.
+        layer(mask, vertex, HN, inlier_thresh=THRESH, seed=999).result()
+    lib.pvb_profile_enable(args.profile_every)     # stage events on every n-th step only: each record drains the pipeline
     if sampler is not None:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

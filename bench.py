@@ -162,6 +162,27 @@ def _usable_cores():
     return n
 
 
+def _bind_to_gpu_numa_node(index):
+    """One process per GPU on a two-socket box: run this rank's host thread -- and therefore allocate its pinned buffers --
+    on the CPUs NVML lists as local to its GPU (`nvidia-smi topo -m`, "CPU Affinity"), so that the end-to-end path's PCIe
+    reads do not cross the socket interconnect.  Best effort: returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if len(cpus) >= 2:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def _cpu_baseline(mask, vertex, K, seconds_target=15.0):
     """Oracle port (oracle/pvnet_oracle.c) on the host cores: one image per thread at a time."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -216,6 +237,7 @@ def run_ours(args):
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_to_gpu_numa_node(local) if world > 1 else None
     lib = _lib.load()
     wl = args.workload
     cfg = synth.CONFIGS[wl]
@@ -526,6 +548,7 @@ def run_ours(args):
             "stages_ms": {"select": stage_ms[0], "generate": stage_ms[1], "vote": stage_ms[2], "refit": stage_ms[3],
                           "profiled_steps": calls, "note": f"CUDA events at the stage boundaries of every {args.profile_every}-th timed step"},
             "host": {"enqueue_ms_per_step": (t_host1 - t_host0) * 1e3 / args.steps, "usable_cores": _usable_cores(),
+                     "bound_to_gpu_local_cpus": numa,
                      "note": "host time spent enqueueing one step (rank 0); if it approaches ms_per_step the GPU is launch-starved"},
             "extras": extras,
         }

@@ -38,7 +38,7 @@ UNIT = "images*keypoints/s"
 WORKLOAD = "cfg2"
 HN = 512
 THRESH = 0.99
-KERNELS_PER_STEP = 6   # mask_bits, thin_scan, gather, generate, vote, refit (+1 exchange_wait per step when N > 1)
+KERNELS_PER_STEP = 5   # mask_bits, thin_gather, generate, vote, refit (+1 exchange_wait per step when N > 1)
 
 
 def workload_string(name, cfg, layout, per_gpu_images):

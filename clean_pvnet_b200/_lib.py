@@ -33,7 +33,7 @@ class PvbDesc(ctypes.Structure):
 
 class PvbLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in
-                ("total", "status", "fgsum", "nz", "tn", "state", "bits", "wordoff", "blocktot", "xy", "dirs", "hyp",
+                ("total", "status", "fgsum", "nz", "tn", "state", "bits", "ticket", "blocktot", "xy", "dirs", "hyp",
                  "counts", "win", "refit_partial", "refit_ticket")] + [
                     ("nwords", ctypes.c_int32), ("nblocks", ctypes.c_int32), ("capacity", ctypes.c_int32),
                     ("refit_splits", ctypes.c_int32)]

@@ -96,7 +96,7 @@ int make_layout(const pvb_desc *d, pvb_layout *L)
     if (rc) return rc;
     const size_t B = (size_t)d->B, K = (size_t)d->K, hn = (size_t)d->hn;
     const int nwords = (int)(((long long)d->H * d->W + 31) / 32);
-    const int nblocks = (nwords + 127) / 128;      // == TS_THREADS of select.cu
+    const int nblocks = (nwords + 127) / 128;      // == TS_THREADS of select.cu (one thin_gather CTA per 128 words)
     const int cap = default_capacity(d);
     const int splits = refit_splits_for(cap);
     size_t off = 0;
@@ -108,9 +108,9 @@ int make_layout(const pvb_desc *d, pvb_layout *L)
     L->tn = take(B * sizeof(int));
     L->state = take(B * sizeof(int));
     L->refit_ticket = take(B * K * sizeof(int));
-    L->bits = take(B * nwords * sizeof(uint32_t));
-    L->wordoff = take(B * nwords * sizeof(int));
+    L->ticket = take(B * sizeof(int));
     L->blocktot = take(B * nblocks * sizeof(int));
+    L->bits = take(B * nwords * sizeof(uint32_t));
     L->xy = take(B * cap * sizeof(float2));
     L->dirs = take(B * K * cap * sizeof(float2));
     L->hyp = take(B * K * hn * sizeof(float2));
@@ -155,8 +155,8 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
     s.rowwise_gather = 0;
     s.seg_classes = 0; s.seg_cs = 0; s.mask_out = nullptr;
     s.bits = reinterpret_cast<uint32_t *>(w + L.bits);
-    s.wordoff = reinterpret_cast<int *>(w + L.wordoff);
-    s.blocktot = reinterpret_cast<int *>(w + L.blocktot);
+    s.blocktot = reinterpret_cast<unsigned *>(w + L.blocktot);
+    s.ticket = reinterpret_cast<int *>(w + L.ticket);
     s.fgsum = reinterpret_cast<unsigned long long *>(w + L.fgsum);
     s.nz = reinterpret_cast<int *>(w + L.nz);
     s.tn = reinterpret_cast<int *>(w + L.tn);
@@ -182,7 +182,7 @@ int make_plan(const pvb_desc *d, const void *mask, const float *vertex, const in
 
 int run_select(const Plan &P, cudaStream_t st)
 {
-    // status, fgsum, nz, tn, state, refit tickets: contiguous at the start of the workspace
+    // status, fgsum, nz, tn, state, refit tickets, thin_gather tickets, block totals: contiguous at the start of the workspace
     cudaError_t e = cudaMemsetAsync(P.s.status, 0, P.L.bits, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(header)");
     e = launch_select(P.s, st);

@@ -21,7 +21,8 @@ struct SelectArgs {
     uint64_t seed;
     uint32_t tag_sel;
     uint32_t *bits;
-    int *wordoff, *blocktot;
+    unsigned *blocktot;           // [B][nblocks] block totals | READY bit (zeroed with the header)
+    int *ticket;                  // [B] arrival counter of the thin_gather CTAs (zeroed with the header)
     unsigned long long *fgsum;
     int *nz, *tn, *state, *status;
     float2 *xy, *dirs;

@@ -6,15 +6,14 @@
 //
 // HBM layout produced (see pvb_layout in include/pvnet_vote_b200.h):
 //   bits    uint32[B][nwords]      1 bit per pixel, row-major
-//   wordoff int32 [B][nwords]      exclusive popcount prefix inside each 128-word block
-//   blocktot int32[B][nblocks]     selected pixels per 128-word block  -> order-preserving compaction
+//   blocktot uint32[B][nblocks]    selected pixels per 128-word block | READY bit -> order-preserving compaction by
+//                                  decoupled look-back (thin_gather_kernel)
 //   xy      float2[B][cap]         (x,y) of the t-th selected pixel (torch.nonzero order, :140-141)
 //   dirs    float2[B][K][cap]      vertex vectors of the selected pixels, keypoint-major so that a
 //                                  (image,keypoint) vote CTA streams one contiguous float2 array
 //
-// All three kernels are HBM/latency bound: the mask is read exactly once (mask_bits), the
-// bitmap (1/256 of an int64 mask) is what later passes touch, and the vertex field is read
-// only at selected pixels.
+// Both kernels are HBM/latency bound: the mask is read exactly once (mask_bits), the bitmap (1/256 of an int64 mask)
+// is what the second pass touches, and the vertex field is read only at selected pixels.
 #include <atomic>
 #include "common.cuh"
 #include "kernels.h"
@@ -202,24 +201,50 @@ seg_bits_kernel(const float *__restrict__ seg, long long sb, long long sc, long 
     }
 }
 
-// One CTA per 128 bitmap words: decides skip / thinning for its image (ransac_voting_gpu.py:129-138),
-// applies the Bernoulli thinning to its words, and writes the exclusive popcount prefix WITHIN the
-// block plus the block total; the gather kernel adds the totals of the preceding blocks.
+// thin_gather_kernel -- thinning decision, ordered compaction and vertex gather of one 128-word block (4096 pixels) in ONE
+// launch (round 1/2a: thin_scan_kernel + gather_kernel with wordoff[] in between).
+//   * decides skip / thinning for its image (ransac_voting_gpu.py:129-138) and applies the Bernoulli thinning to its words;
+//   * in-block exclusive popcount scan -> position of every selected pixel inside the block;
+//   * the offset of the block inside the image (torch.nonzero order needs the totals of all preceding blocks) comes from a
+//     decoupled look-back: every CTA publishes  total | READY  in blocktot[b][blk] as soon as it has scanned its block and
+//     then sums its predecessors' entries, polling the ones that are not there yet.  Block ids are drawn from a per-image
+//     ticket counter in arrival order, so a CTA's predecessors have always started (no reliance on the dispatch order);
+//     the poll is bounded and reports PVB_ERR_CUDA through the status word instead of hanging;
+//   * the block's selected pixels are listed in shared memory and the CTA walks that dense list: one lane per selected
+//     pixel, K independent loads in flight per lane, each store instruction of a warp writes 32 consecutive t of one
+//     keypoint plane of dirs[] (256 B); pinned HOST input is read row-wise (see set_gather_tuning below).
 constexpr int TS_THREADS = 128;
+constexpr int GA_THREADS = TS_THREADS;
+constexpr unsigned LB_READY = 0x80000000u;          // blocktot entry: bit 31 = published, bits 0..30 = selected pixels
 
-__global__ void __launch_bounds__(TS_THREADS)
-thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__restrict__ blocktot,
-                 const unsigned long long *__restrict__ fgsum, int *__restrict__ tn, int *__restrict__ state,
-                 const float *__restrict__ selection, int nwords, int nblocks, int HW, int min_num, int max_num,
-                 uint2 key, uint32_t tag, int img_base)
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p)
 {
-    const int b = blockIdx.y, blk = blockIdx.x;
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(GA_THREADS)
+thin_gather_kernel(uint32_t *__restrict__ bits, unsigned *__restrict__ blocktot, int *__restrict__ ticket,
+                   const unsigned long long *__restrict__ fgsum, int *__restrict__ tn, int *__restrict__ state,
+                   int *__restrict__ status, const float *__restrict__ selection, const float *__restrict__ vertex,
+                   long long sB, long long sH, long long sW, long long sK, long long sC,
+                   float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W, int HW,
+                   int min_num, int max_num, uint2 key, uint32_t tag, int img_base, int rowwise)
+{
+    __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (12 bits)
+    __shared__ int s_base, s_blk;
+    __shared__ int warp_tot[TS_THREADS / 32];
+    const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long fg = fgsum[b];
-    if (fg < (unsigned long long)(min_num < 0 ? 0 : min_num)) {   // :129  (uniform per image)
-        if (tid == 0) { if (blk == 0) state[b] = 1; blocktot[(size_t)b * nblocks + blk] = 0; }
+    if (fg < (unsigned long long)(min_num < 0 ? 0 : min_num)) {   // :129  (uniform per image): nothing to compact
+        if (tid == 0 && blockIdx.x == 0) state[b] = 1;
         return;
     }
+    if (tid == 0) s_blk = atomicAdd(ticket + b, 1);             // block id in arrival order (see above)
+    __syncthreads();
+    const int blk = s_blk;
     const bool thin = fg > (unsigned long long)(max_num < 0 ? 0 : max_num);   // :135
     const float ratio = thin ? __fdiv_rn((float)max_num, (float)fg) : 0.f;     // max_num / fg.float()
     const int w = blk * TS_THREADS + tid;
@@ -249,7 +274,7 @@ thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__
             }
         }
         word = keep;
-        bits[(size_t)b * nwords + w] = word;
+        bits[(size_t)b * nwords + w] = word;                   // the thinned bitmap stays inspectable (debug / tooling)
     }
     const int c = __popc(word);
     int incl = c;
@@ -258,7 +283,6 @@ thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    __shared__ int warp_tot[TS_THREADS / 32];
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     int warp_excl = 0, total = 0;
@@ -268,64 +292,50 @@ thin_scan_kernel(uint32_t *__restrict__ bits, int *__restrict__ wordoff, int *__
         if (i < warp) warp_excl += t;
         total += t;
     }
-    if (w < nwords) wordoff[(size_t)b * nwords + w] = warp_excl + incl - c;
     if (tid == 0) {
-        blocktot[(size_t)b * nblocks + blk] = total;
+        atomicExch(blocktot + (size_t)b * nblocks + blk, (unsigned)total | LB_READY);   // publish first, then look back
         if (total) atomicAdd(tn + b, total);
     }
-}
-
-// One CTA per 128-word block (the thin_scan granularity).  The block's selected pixels are first
-// listed in shared memory (position = the in-block prefix thin_scan left in wordoff[]), then the CTA
-// walks that dense list: every lane is active, loads touch only selected pixels, and each store
-// instruction of a warp writes 32 consecutive t of one keypoint plane of dirs[] (256 B).
-constexpr int GA_THREADS = TS_THREADS;
-
-__global__ void __launch_bounds__(GA_THREADS)
-gather_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ wordoff,
-              const int *__restrict__ blocktot, const int *__restrict__ state, int *__restrict__ tn,
-              int *__restrict__ status, const float *__restrict__ vertex,
-              long long sB, long long sH, long long sW, long long sK, long long sC,
-              float2 *__restrict__ xy, float2 *__restrict__ dirs, int nwords, int nblocks, int K, int cap, int W,
-              int rowwise)
-{
-    __shared__ unsigned short s_list[TS_THREADS * 32];   // pixel index inside the block (12 bits)
-    __shared__ int s_base;
-    const int b = blockIdx.y, blk = blockIdx.x;
-    if (state[b] != 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (blk == 0 && tid == 0 && tn[b] > cap) {
-        // more pixels selected than the workspace holds: report, clamp (nobody in this kernel reads tn)
-        atomicCAS(status, 0, PVB_ERR_CAPACITY);
-        status[1] = b;
-        tn[b] = cap;
-    }
-    const int total = blocktot[(size_t)b * nblocks + blk];
     if (total == 0) return;
-    if (warp == 0) {   // offset of this block = totals of the preceding blocks
+    if (warp == 0) {   // offset of this block = totals of the preceding blocks (decoupled look-back, bounded poll)
         int base = 0;
-        for (int i = lane; i < blk; i += 32) base += blocktot[(size_t)b * nblocks + i];
+        bool ok = true;
+        for (int i = lane; i < blk; i += 32) {
+            const unsigned *p = blocktot + (size_t)b * nblocks + i;
+            unsigned v = ld_volatile_u32(p);
+            for (int spin = 0; !(v & LB_READY); ++spin) {
+                if (spin > (1 << 22)) { ok = false; break; }
+                __nanosleep(20);
+                v = ld_volatile_u32(p);
+            }
+            base += (int)(v & ~LB_READY);
+        }
         base = warp_sum(base);
+        if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicCAS(status, 0, PVB_ERR_CUDA);
         if (lane == 0) s_base = base;
     }
-    const int w = blk * TS_THREADS + tid;
-    const float *vimg = vertex + (long long)b * sB;
-    if (w < nwords) {
-        uint32_t word = bits[(size_t)b * nwords + w];
-        int o = wordoff[(size_t)b * nwords + w];
-        while (word) {
-            const int j = __ffs(word) - 1;
-            word &= word - 1;
+    {
+        int o = warp_excl + incl - c;
+        uint32_t m = word;
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
             s_list[o++] = (unsigned short)(tid * 32 + j);
         }
     }
     __syncthreads();
     const int base = s_base;
+    if (tid == 0 && base + total > cap) {
+        // more pixels selected than the workspace holds: report; the walks below stop at cap and every consumer clamps tn
+        atomicCAS(status, 0, PVB_ERR_CAPACITY);
+        status[1] = b;
+    }
     const bool vec = (sC == 1 && (sK & 1) == 0 && (sW & 1) == 0 && (sH & 1) == 0 && (sB & 1) == 0 &&
                       (reinterpret_cast<uintptr_t>(vertex) & 7u) == 0);
+    const float *vimg = vertex + (long long)b * sB;
     if (rowwise && vec && sK == 2) {
-        // vertex lives in pinned HOST memory (zero-copy entry): consecutive lanes read consecutive float2 of
-        // the same pixel row so each selected pixel costs one contiguous 8*K-byte PCIe read, not K scattered ones
+        // vertex lives in pinned HOST memory (in-place entry): consecutive lanes read consecutive float2 of the same pixel
+        // row so each selected pixel costs one contiguous 8*K-byte PCIe read, not K scattered ones
         const int nel = min(total, max(cap - base, 0)) * K;
         constexpr int U = 4;                       // PCIe reads in flight per thread
         for (int e0 = tid; e0 < nel; e0 += GA_THREADS * U) {
@@ -426,17 +436,12 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 g2(a.nblocks, a.B);
-    thin_scan_kernel<<<g2, TS_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.fgsum, a.tn, a.state, a.selection,
-                                                nwords, a.nblocks, a.H * a.W, a.min_num, a.max_num,
-                                                make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.tag_sel,
-                                                a.img_base);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    dim3 g3(a.nblocks, a.B);
     const int gmode = g_gather_mode.load(std::memory_order_relaxed);
-    gather_kernel<<<g3, GA_THREADS, 0, st>>>(a.bits, a.wordoff, a.blocktot, a.state, a.tn, a.status, a.vertex,
-                                                a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
-                                                a.nblocks, a.K, a.cap, a.W, (a.rowwise_gather || gmode == 2) ? 1 : 0);
+    thin_gather_kernel<<<g2, GA_THREADS, 0, st>>>(a.bits, a.blocktot, a.ticket, a.fgsum, a.tn, a.state, a.status, a.selection,
+                                                  a.vertex, a.vs[0], a.vs[1], a.vs[2], a.vs[3], a.vs[4], a.xy, a.dirs, nwords,
+                                                  a.nblocks, a.K, a.cap, a.W, a.H * a.W, a.min_num, a.max_num,
+                                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)), a.tag_sel, a.img_base,
+                                                  (a.rowwise_gather || gmode == 2) ? 1 : 0);
     return cudaGetLastError();
 }
 

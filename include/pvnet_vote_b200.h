@@ -109,9 +109,9 @@ typedef struct pvb_layout {
     size_t nz;       /* int32[B]   selected-before-thinning count */
     size_t tn;       /* int32[B]   selected pixel count after thinning (0 when skipped) */
     size_t state;    /* int32[B]   0 ok, 1 skipped (fg < min_num) */
-    size_t bits;     /* uint32[B][nwords] selection bitmap, bit j of word w = pixel 32*w+j */
-    size_t wordoff;  /* int32[B][nwords]  exclusive prefix of popcounts inside each 128-word block */
-    size_t blocktot; /* int32[B][nblocks] selected pixels per 128-word block */
+    size_t bits;     /* uint32[B][nwords] selection bitmap (after thinning), bit j of word w = pixel 32*w+j */
+    size_t ticket;   /* int32[B] arrival counter of the compaction CTAs (block ids are drawn in arrival order) */
+    size_t blocktot; /* uint32[B][nblocks] selected pixels per 128-word block | bit 31 "published" (decoupled look-back) */
     size_t xy;       /* float2[B][capacity]   (x,y) of the t-th selected pixel, row-major (torch.nonzero) order */
     size_t dirs;     /* float2[B][K][capacity] gathered vertex vectors (k-major) */
     size_t hyp;      /* float2[B][K][hn] */

@@ -53,7 +53,7 @@ def test_workspace_layout(pvb):
     assert lib.pvb_workspace_layout(d, L) == 0
     assert L.nwords == 480 * 640 // 32
     assert L.capacity % 32 == 0 and 30000 < L.capacity < 32000      # max_num + 8 sigma + slack
-    offs = [L.status, L.fgsum, L.nz, L.tn, L.state, L.bits, L.wordoff, L.xy, L.dirs, L.hyp, L.counts, L.win, L.total]
+    offs = [L.status, L.fgsum, L.nz, L.tn, L.state, L.ticket, L.blocktot, L.bits, L.xy, L.dirs, L.hyp, L.counts, L.win, L.total]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
     assert L.dirs - L.xy >= 16 * L.capacity * 8
     assert L.hyp - L.dirs >= 16 * 9 * L.capacity * 8

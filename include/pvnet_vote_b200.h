@@ -280,7 +280,7 @@ PVB_API int pvb_exchange_destroy(pvb_exchange *ex);
  * two kernels, ~3 us each on B200: sample with n > 1 to keep the profile out of a measurement).  pvb_profile_read()
  * synchronises those events and ADDS the elapsed milliseconds of every profiled call since the last pvb_profile_reset()
  * into ms[PVB_STAGE_COUNT], returning the number of calls accumulated.  Per host thread. */
-enum { PVB_STAGE_SELECT = 0,   /* mask_bits + select_scan + gather */
+enum { PVB_STAGE_SELECT = 0,   /* mask_bits + thin_gather (thinning, ordered compaction, vertex gather) */
        PVB_STAGE_GENERATE = 1, /* hypothesis generation */
        PVB_STAGE_VOTE = 2,     /* counts memset + vote kernel (the dominant kernel) */
        PVB_STAGE_FINISH = 3,   /* winner + refit, or covariance */
